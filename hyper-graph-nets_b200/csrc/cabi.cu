@@ -1,0 +1,124 @@
+// C-ABI entry points of libhgn_b200.so that are not defined next to their kernels: error state,
+// device probe, MLP-tile dispatch (fp32 FFMA parity path vs bf16 tcgen05 path) and host<->device copies.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace hgn {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+// fp32 path (mlp_f32.cu)
+size_t mlp_f32_packed_bytes(int n_chunks);
+int mlp_f32_pack(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                 const float* b2, const float* gamma, const float* beta, void* packed, cudaStream_t st);
+int mlp_f32_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
+                    cudaStream_t st);
+size_t mlp_f32_backward_workspace_bytes(int64_t rows, int n_chunks);
+int mlp_f32_backward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* grad_out, int resid_chunk, void* const* grad_chunk,
+                     float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+// bf16 tcgen05 path (mlp_tc.cu)
+size_t mlp_tc_packed_bytes(int n_chunks);
+int mlp_tc_pack(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                const float* b2, const float* gamma, const float* beta, void* packed, cudaStream_t st);
+int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
+                   cudaStream_t st);
+size_t mlp_tc_backward_workspace_bytes(int64_t rows, int n_chunks);
+int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* grad_out, int resid_chunk, void* const* grad_chunk,
+                    float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+static int check_chunks(const hgn_chunks* ch, const char* who) {
+  HGN_CHECK_ARG(ch != nullptr, "%s: chunks is NULL", who);
+  HGN_CHECK_ARG(ch->n_chunks >= 1 && ch->n_chunks <= HGN_MAX_CHUNKS, "%s: n_chunks=%d outside [1,%d]", who, ch->n_chunks, HGN_MAX_CHUNKS);
+  for (int c = 0; c < ch->n_chunks; ++c) HGN_CHECK_ARG(ch->src[c] != nullptr, "%s: chunk %d has no source", who, c);
+  return HGN_OK;
+}
+
+}  // namespace hgn
+
+using namespace hgn;
+
+extern "C" int hgn_abi_version(void) { return HGN_B200_ABI_VERSION; }
+extern "C" const char* hgn_last_error(void) { return g_error; }
+
+extern "C" int hgn_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" size_t hgn_mlp_packed_bytes(int dtype, int32_t n_chunks) {
+  if (n_chunks < 1 || n_chunks > HGN_MAX_CHUNKS) return 0;
+  return dtype == HGN_BF16 ? mlp_tc_packed_bytes(n_chunks) : mlp_f32_packed_bytes(n_chunks);
+}
+
+extern "C" int hgn_mlp_pack(int dtype, int32_t n_chunks, const float* W0, const float* b0, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* gamma, const float* beta, void* packed, void* stream) {
+  HGN_CHECK_ARG(n_chunks >= 1 && n_chunks <= HGN_MAX_CHUNKS, "mlp_pack: n_chunks=%d", n_chunks);
+  HGN_CHECK_ARG(W0 && b0 && W1 && b1 && W2 && b2 && gamma && beta && packed, "mlp_pack: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32) return mlp_f32_pack(n_chunks, W0, b0, W1, b1, W2, b2, gamma, beta, packed, st);
+  if (dtype == HGN_BF16) return mlp_tc_pack(n_chunks, W0, b0, W1, b1, W2, b2, gamma, beta, packed, st);
+  set_error("mlp_pack: unknown dtype %d", dtype);
+  return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_mlp_forward(int dtype, int64_t rows, const hgn_chunks* chunks, const void* packed, const void* resid,
+                               int64_t resid_row_offset, void* out, void* stream) {
+  if (int rc = check_chunks(chunks, "mlp_forward")) return rc;
+  HGN_CHECK_ARG(rows >= 0 && rows < (int64_t(1) << 31), "mlp_forward: rows=%lld", (long long)rows);
+  if (rows == 0) return HGN_OK;
+  HGN_CHECK_ARG(packed && resid && out, "mlp_forward: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32) return mlp_f32_forward(rows, chunks, packed, resid, resid_row_offset, out, st);
+  if (dtype == HGN_BF16) return mlp_tc_forward(rows, chunks, packed, resid, resid_row_offset, out, st);
+  set_error("mlp_forward: unknown dtype %d", dtype);
+  return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" size_t hgn_mlp_backward_workspace_bytes(int dtype, int64_t rows, int32_t n_chunks) {
+  if (n_chunks < 1 || n_chunks > HGN_MAX_CHUNKS || rows < 0) return 0;
+  return dtype == HGN_BF16 ? mlp_tc_backward_workspace_bytes(rows, n_chunks) : mlp_f32_backward_workspace_bytes(rows, n_chunks);
+}
+
+extern "C" int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunks, const void* packed, const void* grad_out,
+                                int32_t resid_chunk, void* const* grad_chunk, float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
+                                float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (int rc = check_chunks(chunks, "mlp_backward")) return rc;
+  HGN_CHECK_ARG(rows >= 0 && rows < (int64_t(1) << 31), "mlp_backward: rows=%lld", (long long)rows);
+  HGN_CHECK_ARG(packed && workspace && grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta,
+                "mlp_backward: null pointer");
+  HGN_CHECK_ARG(rows == 0 || grad_out, "mlp_backward: grad_out is NULL");
+  HGN_CHECK_ARG(resid_chunk >= -1 && resid_chunk < chunks->n_chunks, "mlp_backward: resid_chunk=%d", resid_chunk);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32)
+    return mlp_f32_backward(rows, chunks, packed, grad_out, resid_chunk, grad_chunk, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
+                            grad_gamma, grad_beta, workspace, workspace_bytes, st);
+  if (dtype == HGN_BF16)
+    return mlp_tc_backward(rows, chunks, packed, grad_out, resid_chunk, grad_chunk, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
+                           grad_gamma, grad_beta, workspace, workspace_bytes, st);
+  set_error("mlp_backward: unknown dtype %d", dtype);
+  return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream) {
+  HGN_CUDA_OK(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return HGN_OK;
+}
+extern "C" int hgn_copy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream) {
+  HGN_CUDA_OK(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return HGN_OK;
+}

@@ -1,0 +1,467 @@
+// Receiver-sorted CSR plan + deterministic segmented reductions (no floating-point atomics).
+//
+// HBM-bound kernels.  Layout: edge rows [E, D] row-major, one warp per segment row; a lane owns 4
+// consecutive features so every row access is one coalesced 512-byte (fp32) / 256-byte (bf16)
+// request, stores are 128-bit (fp32) / 64-bit (bf16) vectors.  The edges of a segment are visited in
+// ascending edge id (stable sort), so sums have a fixed association order and max/min ties resolve
+// to the first edge, like torch_scatter's CPU reducer (src/util.py:117-127 call sites).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace hgn {
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+__global__ void csr_prepare_kernel(const int64_t* __restrict__ ids, int64_t E, int64_t S, int32_t* __restrict__ ids32,
+                                   int32_t* __restrict__ iota, int32_t* __restrict__ counts, int32_t* __restrict__ bad) {
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= E) return;
+  int64_t v = ids[i];
+  if (v < 0 || v >= S) {
+    atomicExch(bad, 1);
+    v = 0;
+  }
+  ids32[i] = int32_t(v);
+  iota[i] = int32_t(i);
+  atomicAdd(&counts[v], 1);   // integer atomics: the result does not depend on the order
+}
+
+static int sort_bits(int64_t S) {
+  int bits = 1;
+  while ((int64_t(1) << bits) < S) ++bits;
+  return bits;
+}
+
+struct CsrLayout {
+  size_t ids32, keys_out, iota, counts, bad, cub, total;
+  size_t cub_bytes;
+};
+
+static CsrLayout csr_layout(int64_t E, int64_t S) {
+  CsrLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  size_t e = size_t(E > 0 ? E : 1);
+  L.ids32 = take(e * 4);
+  L.keys_out = take(e * 4);
+  L.iota = take(e * 4);
+  L.counts = take(size_t(S + 1) * 4);
+  L.bad = take(4);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, int(e), 0, sort_bits(S));
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, int(S + 1));
+  L.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  L.cub = take(L.cub_bytes);
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: sum / mean / max / min (+ arg) in one pass
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_reduce_vec_kernel(const T* __restrict__ data, int32_t D, const int32_t* __restrict__ perm,
+                          const int32_t* __restrict__ rowptr, int64_t S, T* __restrict__ out_sum, T* __restrict__ out_mean,
+                          T* __restrict__ out_max, T* __restrict__ out_min, int32_t* __restrict__ argmax,
+                          int32_t* __restrict__ argmin, int accumulate_sum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (seg >= S) return;
+  const int beg = rowptr[seg], end = rowptr[seg + 1];
+  const bool want_minmax = (out_max != nullptr) || (out_min != nullptr);
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    int4 amx = make_int4(-1, -1, -1, -1), amn = make_int4(-1, -1, -1, -1);
+    int j = beg;
+    // two rows in flight per lane: the segment (mean in-degree ~6 on triangle meshes) is short, so
+    // memory-level parallelism comes from many warps plus this 2-way unroll
+    for (; j + 1 < end; j += 2) {
+      const int e0 = perm[j], e1 = perm[j + 1];
+      const float4 a = load4(data + int64_t(e0) * D + c);
+      const float4 b = load4(data + int64_t(e1) * D + c);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+      if (want_minmax) {
+#define HGN_MINMAX(v, e)                                              \
+        if (v.x > mx.x) { mx.x = v.x; amx.x = e; } if (v.y > mx.y) { mx.y = v.y; amx.y = e; } \
+        if (v.z > mx.z) { mx.z = v.z; amx.z = e; } if (v.w > mx.w) { mx.w = v.w; amx.w = e; } \
+        if (v.x < mn.x) { mn.x = v.x; amn.x = e; } if (v.y < mn.y) { mn.y = v.y; amn.y = e; } \
+        if (v.z < mn.z) { mn.z = v.z; amn.z = e; } if (v.w < mn.w) { mn.w = v.w; amn.w = e; }
+        HGN_MINMAX(a, e0)
+        HGN_MINMAX(b, e1)
+      }
+    }
+    if (j < end) {
+      const int e0 = perm[j];
+      const float4 a = load4(data + int64_t(e0) * D + c);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      if (want_minmax) { HGN_MINMAX(a, e0) }
+    }
+#undef HGN_MINMAX
+    const int64_t o = seg * D + c;
+    if (out_sum) {
+      float4 r = s;
+      if (accumulate_sum) { float4 p = load4(out_sum + o); r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+      store4(out_sum + o, r);
+    }
+    if (out_mean) {
+      const float inv = 1.0f / float(max(end - beg, 1));
+      store4(out_mean + o, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+    }
+    if (end == beg) { mx = make_float4(0.f, 0.f, 0.f, 0.f); mn = mx; }   // empty segment -> 0
+    if (out_max) store4(out_max + o, mx);
+    if (out_min) store4(out_min + o, mn);
+    if (argmax) *reinterpret_cast<int4*>(argmax + o) = amx;
+    if (argmin) *reinterpret_cast<int4*>(argmin + o) = amn;
+  }
+}
+
+template <typename T>
+__global__ void segment_reduce_scalar_kernel(const T* __restrict__ data, int32_t D, const int32_t* __restrict__ perm,
+                                             const int32_t* __restrict__ rowptr, int64_t S, T* out_sum, T* out_mean,
+                                             T* out_max, T* out_min, int32_t* argmax, int32_t* argmin, int accumulate_sum) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= S * D) return;
+  const int64_t seg = i / D;
+  const int c = int(i - seg * D);
+  const int beg = rowptr[seg], end = rowptr[seg + 1];
+  float s = 0.f, mx = -INFINITY, mn = INFINITY;
+  int amx = -1, amn = -1;
+  for (int j = beg; j < end; ++j) {
+    const int e = perm[j];
+    const float v = to_f(data[int64_t(e) * D + c]);
+    s += v;
+    if (v > mx) { mx = v; amx = e; }
+    if (v < mn) { mn = v; amn = e; }
+  }
+  if (end == beg) { mx = 0.f; mn = 0.f; }
+  if (out_sum) out_sum[i] = from_f<T>(accumulate_sum ? s + to_f(out_sum[i]) : s);
+  if (out_mean) out_mean[i] = from_f<T>(s / float(max(end - beg, 1)));
+  if (out_max) out_max[i] = from_f<T>(mx);
+  if (out_min) out_min[i] = from_f<T>(mn);
+  if (argmax) argmax[i] = amx;
+  if (argmin) argmin[i] = amn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: one warp per edge row, gathers the receiver's gradient rows
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_reduce_bwd_vec_kernel(int64_t E, int32_t D, const int32_t* __restrict__ ids, const int32_t* __restrict__ rowptr,
+                              const T* __restrict__ g_sum, const T* __restrict__ g_mean, const T* __restrict__ g_max,
+                              const T* __restrict__ g_min, const int32_t* __restrict__ argmax,
+                              const int32_t* __restrict__ argmin, T* __restrict__ grad, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (e >= E) return;
+  const int r = ids[e];
+  const float inv = g_mean ? 1.0f / float(max(rowptr[r + 1] - rowptr[r], 1)) : 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const int64_t o = int64_t(r) * D + c;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g_sum) { const float4 a = load4(g_sum + o); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+    if (g_mean) { const float4 a = load4(g_mean + o); g.x += a.x * inv; g.y += a.y * inv; g.z += a.z * inv; g.w += a.w * inv; }
+    if (g_max) {
+      const float4 a = load4(g_max + o);
+      const int4 w = *reinterpret_cast<const int4*>(argmax + o);
+      if (w.x == e) g.x += a.x; if (w.y == e) g.y += a.y; if (w.z == e) g.z += a.z; if (w.w == e) g.w += a.w;
+    }
+    if (g_min) {
+      const float4 a = load4(g_min + o);
+      const int4 w = *reinterpret_cast<const int4*>(argmin + o);
+      if (w.x == e) g.x += a.x; if (w.y == e) g.y += a.y; if (w.z == e) g.z += a.z; if (w.w == e) g.w += a.w;
+    }
+    const int64_t q = e * D + c;
+    if (accumulate) { const float4 p = load4(grad + q); g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w; }
+    store4(grad + q, g);
+  }
+}
+
+template <typename T>
+__global__ void segment_reduce_bwd_scalar_kernel(int64_t E, int32_t D, const int32_t* ids, const int32_t* rowptr,
+                                                 const T* g_sum, const T* g_mean, const T* g_max, const T* g_min,
+                                                 const int32_t* argmax, const int32_t* argmin, T* grad, int accumulate) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= E * D) return;
+  const int64_t e = i / D;
+  const int c = int(i - e * D);
+  const int r = ids[e];
+  const int64_t o = int64_t(r) * D + c;
+  float g = 0.f;
+  if (g_sum) g += to_f(g_sum[o]);
+  if (g_mean) g += to_f(g_mean[o]) / float(max(rowptr[r + 1] - rowptr[r], 1));
+  if (g_max && argmax[o] == e) g += to_f(g_max[o]);
+  if (g_min && argmin[o] == e) g += to_f(g_min[o]);
+  if (accumulate) g += to_f(grad[i]);
+  grad[i] = from_f<T>(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo rows
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rows_gather_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int32_t D, T* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int64_t r = idx[i];
+  for (int c = lane * 4; c < D; c += 128) store4(dst + i * D + c, load4(src + r * D + c));
+}
+template <typename T>
+__global__ void rows_scatter_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int32_t D, T* __restrict__ dst, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int64_t r = idx[i];
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v = load4(src + i * D + c);
+    if (accumulate) { const float4 p = load4(dst + r * D + c); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    store4(dst + r * D + c, v);
+  }
+}
+
+template <typename T>
+static int segment_reduce_impl(const T* data, int64_t E, int32_t D, const int32_t* perm, const int32_t* rowptr, int64_t S,
+                               T* out_sum, T* out_mean, T* out_max, T* out_min, int32_t* argmax, int32_t* argmin,
+                               int accumulate_sum, cudaStream_t st) {
+  if (S == 0) return HGN_OK;
+  if (D % 4 == 0) {
+    const int64_t blocks = ceil_div(S * 32, 256);
+    segment_reduce_vec_kernel<T><<<unsigned(blocks), 256, 0, st>>>(data, D, perm, rowptr, S, out_sum, out_mean, out_max,
+                                                                out_min, argmax, argmin, accumulate_sum);
+  } else {
+    const int64_t blocks = ceil_div(S * D, 256);
+    segment_reduce_scalar_kernel<T><<<unsigned(blocks), 256, 0, st>>>(data, D, perm, rowptr, S, out_sum, out_mean, out_max,
+                                                                   out_min, argmax, argmin, accumulate_sum);
+  }
+  HGN_LAUNCH_OK("segment_reduce");
+  return HGN_OK;
+}
+
+template <typename T>
+static int segment_reduce_bwd_impl(int64_t E, int32_t D, const int32_t* ids, const int32_t* rowptr, const T* g_sum,
+                                   const T* g_mean, const T* g_max, const T* g_min, const int32_t* argmax,
+                                   const int32_t* argmin, T* grad, int accumulate, cudaStream_t st) {
+  if (E == 0) return HGN_OK;
+  if (D % 4 == 0) {
+    segment_reduce_bwd_vec_kernel<T><<<unsigned(ceil_div(E * 32, 256)), 256, 0, st>>>(E, D, ids, rowptr, g_sum, g_mean, g_max,
+                                                                                   g_min, argmax, argmin, grad, accumulate);
+  } else {
+    segment_reduce_bwd_scalar_kernel<T><<<unsigned(ceil_div(E * D, 256)), 256, 0, st>>>(E, D, ids, rowptr, g_sum, g_mean, g_max,
+                                                                                     g_min, argmax, argmin, grad, accumulate);
+  }
+  HGN_LAUNCH_OK("segment_reduce_bwd");
+  return HGN_OK;
+}
+
+}  // namespace hgn
+
+using namespace hgn;
+
+extern "C" size_t hgn_csr_workspace_bytes(int64_t E, int64_t S) { return csr_layout(E, S).total; }
+
+extern "C" int hgn_csr_build(const int64_t* segment_ids, int64_t E, int64_t S, int32_t* perm, int32_t* rowptr, int32_t* ids32,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  HGN_CHECK_ARG(E >= 0 && S >= 0 && E < (int64_t(1) << 31) && S < (int64_t(1) << 31) - 1, "csr_build: E=%lld S=%lld out of int32 range", (long long)E, (long long)S);
+  HGN_CHECK_ARG(perm && rowptr && workspace, "csr_build: null output/workspace");
+  const CsrLayout L = csr_layout(E, S);
+  if (workspace_bytes < L.total) { set_error("csr_build: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  int32_t* w_ids = reinterpret_cast<int32_t*>(ws + L.ids32);
+  int32_t* w_keys = reinterpret_cast<int32_t*>(ws + L.keys_out);
+  int32_t* w_iota = reinterpret_cast<int32_t*>(ws + L.iota);
+  int32_t* w_counts = reinterpret_cast<int32_t*>(ws + L.counts);
+  int32_t* w_bad = reinterpret_cast<int32_t*>(ws + L.bad);
+  HGN_CUDA_OK(cudaMemsetAsync(w_counts, 0, size_t(S + 1) * 4 + 0, st));
+  HGN_CUDA_OK(cudaMemsetAsync(w_bad, 0, 4, st));
+  if (E > 0) {
+    csr_prepare_kernel<<<unsigned(ceil_div(E, 256)), 256, 0, st>>>(segment_ids, E, S, w_ids, w_iota, w_counts, w_bad);
+    HGN_LAUNCH_OK("csr_prepare");
+  }
+  size_t cub_bytes = L.cub_bytes;
+  HGN_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws + L.cub, cub_bytes, w_counts, rowptr, int(S + 1), st));
+  if (E > 0) {
+    cub_bytes = L.cub_bytes;
+    HGN_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, (const int32_t*)w_ids, w_keys, (const int32_t*)w_iota, perm,
+                                                int(E), 0, sort_bits(S), st));
+    if (ids32) HGN_CUDA_OK(cudaMemcpyAsync(ids32, w_ids, size_t(E) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  int32_t bad = 0;
+  HGN_CUDA_OK(cudaMemcpyAsync(&bad, w_bad, 4, cudaMemcpyDeviceToHost, st));
+  HGN_CUDA_OK(cudaStreamSynchronize(st));
+  HGN_CHECK_ARG(bad == 0, "csr_build: segment id outside [0, %lld)", (long long)S);
+  return HGN_OK;
+}
+
+extern "C" int hgn_segment_reduce(int dtype, const void* data, int64_t E, int32_t D, const int32_t* perm, const int32_t* rowptr,
+                                  int64_t S, void* out_sum, void* out_mean, void* out_max, void* out_min, int32_t* argmax,
+                                  int32_t* argmin, int accumulate_sum, void* stream) {
+  HGN_CHECK_ARG(D >= 1 && E >= 0 && S >= 0, "segment_reduce: bad sizes");
+  HGN_CHECK_ARG(rowptr && (E == 0 || (data && perm)), "segment_reduce: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32)
+    return segment_reduce_impl<float>((const float*)data, E, D, perm, rowptr, S, (float*)out_sum, (float*)out_mean, (float*)out_max,
+                                      (float*)out_min, argmax, argmin, accumulate_sum, st);
+  if (dtype == HGN_BF16)
+    return segment_reduce_impl<__nv_bfloat16>((const __nv_bfloat16*)data, E, D, perm, rowptr, S, (__nv_bfloat16*)out_sum,
+                                              (__nv_bfloat16*)out_mean, (__nv_bfloat16*)out_max, (__nv_bfloat16*)out_min, argmax,
+                                              argmin, accumulate_sum, st);
+  set_error("segment_reduce: unknown dtype %d", dtype);
+  return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_segment_reduce_bwd(int dtype, int64_t E, int32_t D, const int32_t* ids32, const int32_t* rowptr, int64_t S,
+                                      const void* g_sum, const void* g_mean, const void* g_max, const void* g_min,
+                                      const int32_t* argmax, const int32_t* argmin, void* grad_data, int accumulate, void* stream) {
+  HGN_CHECK_ARG(D >= 1 && E >= 0, "segment_reduce_bwd: bad sizes");
+  HGN_CHECK_ARG(E == 0 || (ids32 && rowptr && grad_data), "segment_reduce_bwd: null input");
+  HGN_CHECK_ARG((!g_max || argmax) && (!g_min || argmin), "segment_reduce_bwd: max/min gradients need their arg indices");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32)
+    return segment_reduce_bwd_impl<float>(E, D, ids32, rowptr, (const float*)g_sum, (const float*)g_mean, (const float*)g_max,
+                                          (const float*)g_min, argmax, argmin, (float*)grad_data, accumulate, st);
+  if (dtype == HGN_BF16)
+    return segment_reduce_bwd_impl<__nv_bfloat16>(E, D, ids32, rowptr, (const __nv_bfloat16*)g_sum, (const __nv_bfloat16*)g_mean,
+                                                  (const __nv_bfloat16*)g_max, (const __nv_bfloat16*)g_min, argmax, argmin,
+                                                  (__nv_bfloat16*)grad_data, accumulate, st);
+  set_error("segment_reduce_bwd: unknown dtype %d", dtype);
+  return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_rows_gather(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst, void* stream) {
+  HGN_CHECK_ARG(D % 4 == 0 && n >= 0, "rows_gather: D must be a multiple of 4");
+  if (n == 0) return HGN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32) rows_gather_kernel<float><<<unsigned(ceil_div(n * 32, 256)), 256, 0, st>>>((const float*)src, idx, n, D, (float*)dst);
+  else rows_gather_kernel<__nv_bfloat16><<<unsigned(ceil_div(n * 32, 256)), 256, 0, st>>>((const __nv_bfloat16*)src, idx, n, D, (__nv_bfloat16*)dst);
+  HGN_LAUNCH_OK("rows_gather");
+  return HGN_OK;
+}
+
+extern "C" int hgn_rows_scatter(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst, int accumulate, void* stream) {
+  HGN_CHECK_ARG(D % 4 == 0 && n >= 0, "rows_scatter: D must be a multiple of 4");
+  if (n == 0) return HGN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_F32) rows_scatter_kernel<float><<<unsigned(ceil_div(n * 32, 256)), 256, 0, st>>>((const float*)src, idx, n, D, (float*)dst, accumulate);
+  else rows_scatter_kernel<__nv_bfloat16><<<unsigned(ceil_div(n * 32, 256)), 256, 0, st>>>((const __nv_bfloat16*)src, idx, n, D, (__nv_bfloat16*)dst, accumulate);
+  HGN_LAUNCH_OK("rows_scatter");
+  return HGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (LayerNorm beta / bias gradients): per-block partials, then a fixed-order second stage
+// ------------------------------------------------------------------------------------------------
+namespace hgn {
+constexpr int kColsumRowsPerBlock = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int32_t D, float* __restrict__ partial) {
+  // thread (cx, ry): column group cx (4 columns), row lane ry; D/4 column groups x (256/(D/4)) row lanes
+  __shared__ float red[256 * 4];
+  const int groups = D / 4;
+  const int lanes = 256 / groups;
+  const int cx = threadIdx.x % groups, ry = threadIdx.x / groups;
+  const int64_t r0 = int64_t(blockIdx.x) * kColsumRowsPerBlock;
+  const int64_t r1 = min(rows, r0 + kColsumRowsPerBlock);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ry < lanes)
+    for (int64_t r = r0 + ry; r < r1; r += lanes) {
+      const float4 v = load4(x + r * D + cx * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  red[threadIdx.x * 4 + 0] = s.x; red[threadIdx.x * 4 + 1] = s.y; red[threadIdx.x * 4 + 2] = s.z; red[threadIdx.x * 4 + 3] = s.w;
+  __syncthreads();
+  if (threadIdx.x < D) {
+    const int g = threadIdx.x / 4, k = threadIdx.x % 4;
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(l * groups + g) * 4 + k];
+    partial[int64_t(blockIdx.x) * D + threadIdx.x] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t blocks, int32_t D, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float t = 0.f;
+  for (int64_t b = 0; b < blocks; ++b) t += partial[b * D + c];
+  out[c] = t;
+}
+}  // namespace hgn
+
+extern "C" size_t hgn_colsum_workspace_bytes(int64_t rows, int32_t D) {
+  return size_t(hgn::ceil_div(rows > 0 ? rows : 1, hgn::kColsumRowsPerBlock)) * size_t(D) * 4;
+}
+
+extern "C" int hgn_colsum(int dtype, const void* x, int64_t rows, int32_t D, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  HGN_CHECK_ARG(D >= 4 && D % 4 == 0 && D <= 256 && 256 % (D / 4) == 0, "colsum: D=%d must divide 1024 and be <= 256", D);
+  HGN_CHECK_ARG(out && rows >= 0, "colsum: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) { HGN_CUDA_OK(cudaMemsetAsync(out, 0, size_t(D) * 4, st)); return HGN_OK; }
+  const int64_t blocks = hgn::ceil_div(rows, hgn::kColsumRowsPerBlock);
+  if (workspace_bytes < size_t(blocks) * D * 4 || !workspace) { hgn::set_error("colsum: workspace too small"); return HGN_ERR_WORKSPACE; }
+  float* partial = static_cast<float*>(workspace);
+  if (dtype == HGN_F32) hgn::colsum_partial_kernel<float><<<unsigned(blocks), 256, 0, st>>>((const float*)x, rows, D, partial);
+  else if (dtype == HGN_BF16) hgn::colsum_partial_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, st>>>((const __nv_bfloat16*)x, rows, D, partial);
+  else { hgn::set_error("colsum: unknown dtype %d", dtype); return HGN_ERR_INVALID_ARGUMENT; }
+  hgn::colsum_final_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, blocks, D, out);
+  HGN_LAUNCH_OK("colsum");
+  return HGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-source segment sum (gather backward): one rounding, fixed order
+// ------------------------------------------------------------------------------------------------
+namespace hgn {
+template <typename T>
+__global__ void __launch_bounds__(256)
+multi_segment_sum_kernel(hgn_segment_sources ms, int64_t S, int32_t D, const T* __restrict__ base, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (seg >= S) return;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base) s = load4(base + seg * D + c);
+    for (int k = 0; k < ms.n_sources; ++k) {
+      const T* data = static_cast<const T*>(ms.data[k]);
+      const int32_t* perm = ms.perm[k];
+      const int beg = ms.rowptr[k][seg], end = ms.rowptr[k][seg + 1];
+      int j = beg;
+      for (; j + 1 < end; j += 2) {
+        const float4 a = load4(data + int64_t(perm[j]) * D + c);
+        const float4 b = load4(data + int64_t(perm[j + 1]) * D + c);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+      }
+      if (j < end) {
+        const float4 a = load4(data + int64_t(perm[j]) * D + c);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+    }
+    store4(out + seg * D + c, s);
+  }
+}
+}  // namespace hgn
+
+extern "C" int hgn_multi_segment_sum(int dtype, const hgn_segment_sources* sources, int64_t S, int32_t D, const void* base,
+                                     void* out, void* stream) {
+  HGN_CHECK_ARG(sources && sources->n_sources >= 0 && sources->n_sources <= 4, "multi_segment_sum: bad sources");
+  HGN_CHECK_ARG(D >= 4 && D % 4 == 0 && S >= 0 && out, "multi_segment_sum: D must be a multiple of 4");
+  if (S == 0) return HGN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = unsigned(hgn::ceil_div(S * 32, 256));
+  if (dtype == HGN_F32) hgn::multi_segment_sum_kernel<float><<<blocks, 256, 0, st>>>(*sources, S, D, (const float*)base, (float*)out);
+  else if (dtype == HGN_BF16) hgn::multi_segment_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*sources, S, D, (const __nv_bfloat16*)base, (__nv_bfloat16*)out);
+  else { hgn::set_error("multi_segment_sum: unknown dtype %d", dtype); return HGN_ERR_INVALID_ARGUMENT; }
+  HGN_LAUNCH_OK("multi_segment_sum");
+  return HGN_OK;
+}

@@ -1,0 +1,45 @@
+"""hgn_b200 -- B200 (sm_100a) message-passing processor behind the reference's ``src/migration`` API.
+
+    from hgn_b200.migration.meshgraphnet import MeshGraphNet      # same ctor / state_dict keys
+    from hgn_b200.util import EdgeSet, MultiGraph, unsorted_segment_operation
+
+``install_as_reference_modules()`` aliases this package as ``src.migration.*`` / ``src.util`` hot-path
+symbols so the reference's own system models (``FlagModel`` ...) run on it unchanged.
+"""
+from .config import precision, set_precision  # noqa: F401
+
+__version__ = '0.1.0'
+
+
+def install_as_reference_modules() -> None:
+    """Make ``import src.migration.meshgraphnet`` etc. resolve to this package.
+
+    Call before importing the reference's ``src.model`` / ``src.algorithms``."""
+    import importlib
+    import sys
+    import types
+
+    src_pkg = sys.modules.get('src')
+    if src_pkg is None:
+        try:
+            src_pkg = importlib.import_module('src')
+        except ImportError:
+            src_pkg = types.ModuleType('src')
+            src_pkg.__path__ = []
+            sys.modules['src'] = src_pkg
+    mig = importlib.import_module('hgn_b200.migration')
+    sys.modules['src.migration'] = mig
+    setattr(src_pkg, 'migration', mig)
+    for name in ('graphnet', 'hypergraphnet', 'heterographnet', 'multiscalegraphnet', 'multigraphnet',
+                 'repeatedgraphnet', 'processor', 'encoder', 'decoder', 'meshgraphnet', 'normalizer'):
+        mod = importlib.import_module(f'hgn_b200.migration.{name}')
+        sys.modules[f'src.migration.{name}'] = mod
+        setattr(mig, name, mod)
+    ref_util = sys.modules.get('src.util')
+    ours = importlib.import_module('hgn_b200.util')
+    if ref_util is not None:
+        # keep the reference's namedtuple classes (its models construct them) and swap the segment op
+        ref_util.unsorted_segment_operation = ours.unsorted_segment_operation
+    else:
+        sys.modules['src.util'] = ours
+        setattr(src_pkg, 'util', ours)

@@ -1,0 +1,47 @@
+"""Mirror of src/migration/processor.py: ``message_passing_steps`` blocks with unshared weights.
+
+Precision: the reference computes in fp32.  ``precision='fp32'`` keeps fp32 storage and fp32 FFMA
+arithmetic (parity mode, 1e-5 relative).  ``precision='bf16'`` converts the latents to bf16 once on
+entry, runs every block on the bf16 tcgen05 kernels (fp32 accumulation, fp32 LayerNorm/residual
+arithmetic) and converts back on exit (throughput mode, 2e-2 relative).  Select it per module
+(``processor.precision = 'bf16'``), globally (``hgn_b200.set_precision``) or with the environment
+variable ``HGN_B200_PRECISION``; no config-schema change is needed.
+"""
+from typing import Callable, List, Type
+
+import torch
+from torch import nn
+
+from .. import config
+from .graphnet import GraphNet
+from ..util import MultiGraph
+
+
+class Processor(nn.Module):
+    """The Graph Neural Network that transforms the input graph."""
+
+    def __init__(self, make_mlp: Callable, output_size: int, message_passing_steps: int,
+                 message_passing_aggregator: str, edge_sets: List[str], graphnet_block: Type[GraphNet]):
+        super().__init__()
+        self.graphnet_blocks = nn.Sequential(*[
+            graphnet_block(model_fn=make_mlp, output_size=output_size,
+                           message_passing_aggregator=message_passing_aggregator, edge_sets=edge_sets)
+            for _ in range(message_passing_steps)])
+        self.precision = None       # None -> hgn_b200.config.precision()
+
+    def forward(self, latent_graph: MultiGraph) -> MultiGraph:
+        precision = self.precision or config.precision()
+        if precision == 'fp32':
+            return self.graphnet_blocks(latent_graph)
+        if precision != 'bf16':
+            raise ValueError(f"unknown precision {precision!r} (expected 'fp32' or 'bf16')")
+        in_dtype = latent_graph.node_features[0].dtype
+        nodes = latent_graph.node_features
+        for i in range(len(nodes)):      # keep the caller's list object, like the blocks do
+            nodes[i] = nodes[i].to(torch.bfloat16)
+        graph = latent_graph._replace(edge_sets=[es._replace(features=es.features.to(torch.bfloat16))
+                                                 for es in latent_graph.edge_sets])
+        graph = self.graphnet_blocks(graph)
+        for i in range(len(graph.node_features)):
+            graph.node_features[i] = graph.node_features[i].to(in_dtype)
+        return graph._replace(edge_sets=[es._replace(features=es.features.to(in_dtype)) for es in graph.edge_sets])

@@ -1,0 +1,298 @@
+"""Autograd glue between torch tensors and the C ABI (``include/hgn_b200.h``).
+
+Two primitives cover every block schedule of the reference's ``src/migration``:
+
+* ``segment_aggregate``  -- ``GraphNet.aggregation`` / ``util.unsorted_segment_operation``
+  (graphnet.py:50-70, util.py:92-134): one kernel pass per edge set yields sum / mean / max / min.
+* ``fused_mlp``          -- gather + MLP + LayerNorm + residual: ``_update_edge_features`` and the
+  ``_update_*node*`` functions (graphnet.py:22-48, 94-124; heterographnet.py:17-33).
+
+torch is used for memory, streams and the autograd graph only; all arithmetic on the path is in
+``libhgn_b200.so``.  Nothing here falls back to torch ops: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import AGG_MAX, AGG_MEAN, AGG_MIN, AGG_SUM, Chunks
+from .plan import SegmentPlan
+
+D_LATENT = 128
+OP_BITS = {"sum": AGG_SUM, "mean": AGG_MEAN, "max": AGG_MAX, "min": AGG_MIN}
+PNA_MASK = AGG_SUM | AGG_MEAN | AGG_MAX | AGG_MIN
+
+# launch counter (bench.py reports "gpu_launches": kernels of ours launched in the timed region)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+class SegmentSources(ctypes.Structure):
+    _fields_ = [("n_sources", ctypes.c_int32), ("data", ctypes.c_void_p * 4), ("perm", ctypes.c_void_p * 4),
+                ("rowptr", ctypes.c_void_p * 4)]
+
+
+# ------------------------------------------------------------------------------------------------
+# segment aggregation
+# ------------------------------------------------------------------------------------------------
+class _SegmentAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data: torch.Tensor, plan: SegmentPlan, mask: int):
+        lib = _cabi.load()
+        _cabi.require_cuda(data)
+        x = data.contiguous()
+        E = x.shape[0]
+        D = 1
+        for n in x.shape[1:]:
+            D *= int(n)
+        assert E == plan.num_elements, "segment plan was built for a different number of elements"
+        S = plan.num_segments
+        out_shape = (S,) + tuple(x.shape[1:])
+        need_arg = bool(mask & (AGG_MAX | AGG_MIN)) and data.requires_grad
+        outs = {}
+        for name, bit in OP_BITS.items():
+            outs[name] = torch.empty(out_shape, dtype=x.dtype, device=x.device) if mask & bit else None
+        argmax = torch.empty(out_shape, dtype=torch.int32, device=x.device) if (need_arg and mask & AGG_MAX) else None
+        argmin = torch.empty(out_shape, dtype=torch.int32, device=x.device) if (need_arg and mask & AGG_MIN) else None
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.hgn_segment_reduce(
+                _cabi.dtype_code(x.dtype), x.data_ptr(), E, D, plan.perm.data_ptr(), plan.rowptr.data_ptr(), S,
+                _cabi.ptr(outs["sum"]), _cabi.ptr(outs["mean"]), _cabi.ptr(outs["max"]), _cabi.ptr(outs["min"]),
+                _cabi.ptr(argmax), _cabi.ptr(argmin), 0, _cabi.stream_ptr()), "hgn_segment_reduce")
+        _count()
+        ctx.plan, ctx.mask, ctx.D, ctx.E = plan, mask, D, E
+        ctx.in_shape = tuple(x.shape)
+        ctx.save_for_backward(*[t for t in (argmax, argmin) if t is not None])
+        ctx.has_argmax, ctx.has_argmin = argmax is not None, argmin is not None
+        return tuple(outs[name] for name in OP_BITS if mask & OP_BITS[name])
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _cabi.load()
+        saved = list(ctx.saved_tensors)
+        argmax = saved.pop(0) if ctx.has_argmax else None
+        argmin = saved.pop(0) if ctx.has_argmin else None
+        plan = ctx.plan
+        g = {}
+        it = iter(grads)
+        for name, bit in OP_BITS.items():
+            gi = next(it) if ctx.mask & bit else None
+            g[name] = gi.contiguous() if gi is not None else None
+        ref = next(t for t in g.values() if t is not None)
+        grad = torch.empty(ctx.in_shape, dtype=ref.dtype, device=ref.device)
+        with torch.cuda.device(ref.device):
+            _cabi.check(lib.hgn_segment_reduce_bwd(
+                _cabi.dtype_code(ref.dtype), ctx.E, ctx.D, plan.ids32.data_ptr(), plan.rowptr.data_ptr(), plan.num_segments,
+                _cabi.ptr(g["sum"]), _cabi.ptr(g["mean"]), _cabi.ptr(g["max"]), _cabi.ptr(g["min"]),
+                _cabi.ptr(argmax), _cabi.ptr(argmin), grad.data_ptr(), 0, _cabi.stream_ptr()), "hgn_segment_reduce_bwd")
+        _count()
+        return grad, None, None
+
+
+def segment_aggregate(data: torch.Tensor, plan: SegmentPlan, ops: Sequence[str]) -> List[torch.Tensor]:
+    """Reductions of ``data[E, ...]`` over the plan's segments, in the order of ``ops``."""
+    mask = 0
+    for op in ops:
+        mask |= OP_BITS[op]
+    res = _SegmentAggregate.apply(data, plan, mask)
+    by_name = dict(zip([n for n in OP_BITS if mask & OP_BITS[n]], res))
+    return [by_name[op] for op in ops]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused gather + MLP + LayerNorm + residual
+# ------------------------------------------------------------------------------------------------
+class ChunkSpec:
+    """One 128-wide slice of the MLP input: rows of ``sources[source]`` either gathered through a plan's
+    ``ids32`` (sender / receiver latents) or taken densely from ``row_offset``."""
+    __slots__ = ("source", "plan", "row_offset")
+
+    def __init__(self, source: int, plan: Optional[SegmentPlan] = None, row_offset: int = 0):
+        self.source, self.plan, self.row_offset = source, plan, row_offset
+
+
+class MLPCall:
+    """Static description of one fused call (not a tensor: passed through autograd untouched)."""
+    __slots__ = ("rows", "chunks", "resid_source", "resid_offset", "packed_cache")
+
+    def __init__(self, rows, chunks, resid_source, resid_offset, packed_cache):
+        self.rows, self.chunks, self.resid_source, self.resid_offset, self.packed_cache = rows, chunks, resid_source, resid_offset, packed_cache
+
+
+def _pack_weights(cache: dict, dtype: torch.dtype, n_chunks: int, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Layout/precision conversion of the eight parameter tensors, redone only when a parameter changed
+    (optimizer steps bump ``_version``)."""
+    key = (dtype, n_chunks)
+    versions = tuple((p.data_ptr(), p._version) for p in params)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == versions:
+        return hit[1]
+    lib = _cabi.load()
+    code = _cabi.dtype_code(dtype)
+    blob = torch.empty(lib.hgn_mlp_packed_bytes(code, n_chunks), dtype=torch.uint8, device=params[0].device)
+    ps = [p.detach().contiguous() for p in params]
+    if any(p.dtype != torch.float32 for p in ps):
+        raise _cabi.HgnError("MLP parameters must be float32 (master weights)")
+    _cabi.check(lib.hgn_mlp_pack(code, n_chunks, *[p.data_ptr() for p in ps], blob.data_ptr(), _cabi.stream_ptr()), "hgn_mlp_pack")
+    _count()
+    cache[key] = (versions, blob)
+    return blob
+
+
+def _fill_chunks(call: MLPCall, sources: Sequence[torch.Tensor]) -> Chunks:
+    ch = Chunks()
+    ch.n_chunks = len(call.chunks)
+    for c, spec in enumerate(call.chunks):
+        ch.src[c] = sources[spec.source].data_ptr()
+        ch.idx[c] = spec.plan.ids32.data_ptr() if spec.plan is not None else None
+        ch.row_offset[c] = spec.row_offset
+    return ch
+
+
+class _FusedMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, call: MLPCall, W0, b0, W1, b1, W2, b2, gamma, beta, *sources):
+        lib = _cabi.load()
+        _cabi.require_cuda(*sources)
+        srcs = [s.contiguous() for s in sources]
+        dtype = srcs[0].dtype
+        n_chunks = len(call.chunks)
+        if W0.shape != (D_LATENT, D_LATENT * n_chunks) or W1.shape != (D_LATENT, D_LATENT) or W2.shape != (D_LATENT, D_LATENT):
+            raise _cabi.HgnError(
+                f"fused MLP kernels are specialised for latent 128: got W0 {tuple(W0.shape)} for {n_chunks} chunks, "
+                f"W1 {tuple(W1.shape)}, W2 {tuple(W2.shape)}")
+        for s in srcs:
+            if s.dtype != dtype or s.shape[-1] != D_LATENT:
+                raise _cabi.HgnError("fused MLP sources must share one dtype and be 128 wide")
+        params = (W0, b0, W1, b1, W2, b2, gamma, beta)
+        with torch.cuda.device(srcs[0].device):
+            packed = _pack_weights(call.packed_cache, dtype, n_chunks, params)
+            ch = _fill_chunks(call, srcs)
+            out = torch.empty((call.rows, D_LATENT), dtype=dtype, device=srcs[0].device)
+            _cabi.check(lib.hgn_mlp_forward(_cabi.dtype_code(dtype), call.rows, ctypes.byref(ch), packed.data_ptr(),
+                                            srcs[call.resid_source].data_ptr(), call.resid_offset, out.data_ptr(),
+                                            _cabi.stream_ptr()), "hgn_mlp_forward")
+        _count()
+        ctx.call = call
+        ctx.packed = packed
+        ctx.n_sources = len(srcs)
+        ctx.save_for_backward(*srcs)
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _cabi.load()
+        call: MLPCall = ctx.call
+        srcs = list(ctx.saved_tensors)
+        dtype = srcs[0].dtype
+        dev = srcs[0].device
+        code = _cabi.dtype_code(dtype)
+        rows = call.rows
+        n_chunks = len(call.chunks)
+        grad_out = grad_out.contiguous()
+        if grad_out.dtype != dtype:
+            grad_out = grad_out.to(dtype)
+        needs = ctx.needs_input_grad[9:]
+
+        # where does each chunk's data gradient go?
+        grad_src: List[Optional[torch.Tensor]] = [None] * len(srcs)
+        chunk_bufs: List[Optional[torch.Tensor]] = [None] * n_chunks
+        dense_owner = {}          # source -> chunk that writes straight into grad_src
+        for c, spec in enumerate(call.chunks):
+            if needs[spec.source] and spec.plan is None and spec.source not in dense_owner:
+                dense_owner[spec.source] = c
+        resid_chunk = -1
+        for s, src in enumerate(srcs):
+            if not needs[s]:
+                continue
+            c = dense_owner.get(s)
+            if c is not None:
+                spec = call.chunks[c]
+                full = spec.row_offset == 0 and rows == src.shape[0]
+                grad_src[s] = torch.empty_like(src) if full else torch.zeros_like(src)
+                chunk_bufs[c] = grad_src[s][spec.row_offset: spec.row_offset + rows]
+                if s == call.resid_source and spec.row_offset == call.resid_offset:
+                    resid_chunk = c
+        for c, spec in enumerate(call.chunks):
+            if needs[spec.source] and chunk_bufs[c] is None:
+                chunk_bufs[c] = torch.empty((rows, D_LATENT), dtype=dtype, device=dev)
+
+        gparams = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes]
+        with torch.cuda.device(dev):
+            ch = _fill_chunks(call, srcs)
+            ws_bytes = lib.hgn_mlp_backward_workspace_bytes(code, rows, n_chunks)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gptrs = (ctypes.c_void_p * n_chunks)(*[b.data_ptr() if b is not None else None for b in chunk_bufs])
+            _cabi.check(lib.hgn_mlp_backward(code, rows, ctypes.byref(ch), ctx.packed.data_ptr(), grad_out.data_ptr(), resid_chunk,
+                                             gptrs, *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
+                        "hgn_mlp_backward")
+            _count()
+            # scatter the gathered chunks back to their source rows (deterministic, one rounding)
+            for s, src in enumerate(srcs):
+                if not needs[s]:
+                    continue
+                gathered = [c for c, spec in enumerate(call.chunks) if spec.source == s and spec.plan is not None]
+                extra_dense = [c for c, spec in enumerate(call.chunks)
+                               if spec.source == s and spec.plan is None and dense_owner.get(s) != c]
+                if gathered:
+                    if grad_src[s] is None:
+                        base = None
+                        grad_src[s] = torch.empty_like(src)
+                    else:
+                        base = grad_src[s]
+                    for i in range(0, len(gathered), 4):
+                        part = gathered[i:i + 4]
+                        ms = SegmentSources()
+                        ms.n_sources = len(part)
+                        for k, c in enumerate(part):
+                            plan = call.chunks[c].plan
+                            ms.data[k] = chunk_bufs[c].data_ptr()
+                            ms.perm[k] = plan.perm.data_ptr()
+                            ms.rowptr[k] = plan.rowptr.data_ptr()
+                        _cabi.check(lib.hgn_multi_segment_sum(code, ctypes.byref(ms), src.shape[0], D_LATENT,
+                                                              _cabi.ptr(base), grad_src[s].data_ptr(), _cabi.stream_ptr()),
+                                    "hgn_multi_segment_sum")
+                        _count()
+                        base = grad_src[s]
+                elif grad_src[s] is None:
+                    grad_src[s] = torch.zeros_like(src)
+                for c in extra_dense:   # same source used densely twice: not on any reference path
+                    off = call.chunks[c].row_offset
+                    grad_src[s][off: off + rows] += chunk_bufs[c]
+            if resid_chunk < 0 and needs[call.resid_source]:
+                s = call.resid_source
+                if grad_src[s] is None:
+                    grad_src[s] = torch.zeros_like(srcs[s])
+                grad_src[s][call.resid_offset: call.resid_offset + rows] += grad_out
+        return (None, *gparams, *grad_src)
+
+
+def fused_mlp(params: Sequence[torch.Tensor], packed_cache: dict, sources: Sequence[torch.Tensor], chunks: Sequence[ChunkSpec],
+              rows: int, resid_source: int, resid_offset: int = 0) -> torch.Tensor:
+    """``out[rows,128] = resid + LayerNorm(MLP([chunk_0 | chunk_1 | ...]))``."""
+    call = MLPCall(int(rows), list(chunks), int(resid_source), int(resid_offset), packed_cache)
+    return _FusedMLP.apply(call, *params, *sources)
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of ``x[rows, D]`` (deterministic)."""
+    lib = _cabi.load()
+    _cabi.require_cuda(x)
+    x = x.contiguous()
+    rows, D = x.shape
+    out = torch.empty(D, dtype=torch.float32, device=x.device)
+    ws_bytes = lib.hgn_colsum_workspace_bytes(rows, D)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.hgn_colsum(_cabi.dtype_code(x.dtype), x.data_ptr(), rows, D, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   _cabi.stream_ptr()), "hgn_colsum")
+    _count(2)
+    return out

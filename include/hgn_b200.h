@@ -1,0 +1,168 @@
+/* libhgn_b200.so -- C ABI of the B200 (sm_100a) message-passing processor kernels.
+ *
+ * The reference (CemOezcan/hyper-graph-nets) has no FFI: its hot path is Python calling ATen and
+ * torch_scatter.  The drop-in boundary is therefore the Python module API of src/migration + src/util
+ * (mirrored by hyper-graph-nets_b200/hgn_b200), and THIS header is what that mirror binds through
+ * ctypes.  Every entry point names the reference code it replaces (paths relative to the reference
+ * root).  Conventions:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns every buffer; nothing is allocated or freed inside; scratch memory is passed in
+ *     and its size is queried with the matching *_workspace_bytes function;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and
+ *     re-entrant across streams (no global mutable state besides the per-thread error string);
+ *   - return value: HGN_OK (0) or a negative hgn_status; hgn_last_error() gives the message;
+ *   - feature rows are row-major contiguous [rows, D]; index arrays are int32 unless stated;
+ *   - dtype: HGN_F32 = fp32 storage and fp32 FFMA arithmetic (parity mode, 1e-5 relative);
+ *            HGN_BF16 = bf16 storage, bf16 tcgen05 tensor-core GEMMs with fp32 TMEM accumulators,
+ *            fp32 bias/ReLU/LayerNorm/residual arithmetic (throughput mode, 2e-2 relative);
+ *   - all reductions are order-deterministic: no floating-point atomics anywhere.
+ */
+#ifndef HGN_B200_H_
+#define HGN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGN_B200_ABI_VERSION 1
+
+typedef enum {
+  HGN_OK = 0,
+  HGN_ERR_INVALID_ARGUMENT = -1,
+  HGN_ERR_CUDA = -2,
+  HGN_ERR_UNSUPPORTED = -3,
+  HGN_ERR_WORKSPACE = -4
+} hgn_status;
+
+typedef enum { HGN_F32 = 0, HGN_BF16 = 1 } hgn_dtype;
+
+/* bit flags selecting segment reductions; 'pna' = all four (src/migration/graphnet.py:52-64) */
+enum { HGN_AGG_SUM = 1, HGN_AGG_MEAN = 2, HGN_AGG_MAX = 4, HGN_AGG_MIN = 8 };
+
+#define HGN_MAX_CHUNKS 24   /* 1 + 4 aggregates x 5 edge sets = 21 for hetero/plate */
+
+int hgn_abi_version(void);
+const char* hgn_last_error(void);
+/* 1 if the current device is an sm_100-class GPU that can run the tcgen05 kernels */
+int hgn_device_supported(void);
+
+/* ---- plan: receiver-sorted CSR --------------------------------------------------------------
+ * Replaces the per-call index expansion of src/util.py:105-110 (repeat_interleave of the int64 ids to
+ * [E,128]) by a one-off stable counting sort.  `segment_ids` are the reference's int64 receivers (or
+ * senders).  Outputs: perm[E] = edge ids grouped by segment, ascending edge id inside a segment
+ * (stable -> "first edge wins" for max/min ties, like torch_scatter's CPU reducer); rowptr[S+1];
+ * ids32[E] = the ids narrowed to int32 (may be NULL).  Ids outside [0,S) are an error reported
+ * through *host_status_flag semantics: the call returns HGN_ERR_INVALID_ARGUMENT after a sync. */
+size_t hgn_csr_workspace_bytes(int64_t num_edges, int64_t num_segments);
+int hgn_csr_build(const int64_t* segment_ids, int64_t num_edges, int64_t num_segments,
+                  int32_t* perm, int32_t* rowptr, int32_t* ids32,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- edge -> node aggregation -----------------------------------------------------------------
+ * Replaces util.unsorted_segment_operation / torch_scatter.scatter_{add,mean,max,min}
+ * (src/util.py:92-134) as used by GraphNet.aggregation (src/migration/graphnet.py:50-70).
+ * One pass over the receiver-sorted edges produces every requested reduction of data[E,D] into
+ * out_*[S,D] (NULL = not requested).  Empty segments give 0; mean = sum / max(count,1);
+ * argmax/argmin[S,D] (int32, -1 for empty segments) record the winning edge id and are required when
+ * max/min are requested with need_arg != 0.  D must be a multiple of 4 for the vector path; any D
+ * >= 1 is accepted (scalar path).  accumulate_sum != 0 adds into out_sum instead of overwriting (used
+ * for the gather backward: dv += segment_sum(dX)). */
+int hgn_segment_reduce(int dtype, const void* data, int64_t num_edges, int32_t D,
+                       const int32_t* perm, const int32_t* rowptr, int64_t num_segments,
+                       void* out_sum, void* out_mean, void* out_max, void* out_min,
+                       int32_t* argmax, int32_t* argmin, int accumulate_sum, void* stream);
+
+/* Backward of the above (autograd of scatter_add / scatter_mean / scatter_max / scatter_min):
+ * grad_data[e,:] (+)= g_sum[r_e,:] + g_mean[r_e,:]/max(cnt_r,1) + [argmax[r_e,:]==e] g_max[r_e,:]
+ *                    + [argmin[r_e,:]==e] g_min[r_e,:]        (NULL gradients are skipped). */
+int hgn_segment_reduce_bwd(int dtype, int64_t num_edges, int32_t D,
+                           const int32_t* ids32, const int32_t* rowptr, int64_t num_segments,
+                           const void* g_sum, const void* g_mean, const void* g_max, const void* g_min,
+                           const int32_t* argmax, const int32_t* argmin,
+                           void* grad_data, int accumulate, void* stream);
+
+/* Backward of the row gathers v[senders], v[receivers] (torch.index_select -> index_add_ with float
+ * atomics in the reference, src/migration/graphnet.py:28-29): out[n,:] = base[n,:] (if base != NULL)
+ * + sum_k sum_{j in segment_k(n)} data_k[perm_k[j], :], accumulated in fp32 in a fixed order
+ * (source k ascending, then ascending element id) and rounded once.  n_sources <= 4; out may alias base. */
+typedef struct {
+  int32_t n_sources;
+  const void* data[4];          /* [E_k, D] rows of dtype */
+  const int32_t* perm[4];       /* CSR permutation of source k */
+  const int32_t* rowptr[4];     /* [S+1] */
+} hgn_segment_sources;
+int hgn_multi_segment_sum(int dtype, const hgn_segment_sources* sources, int64_t num_segments, int32_t D,
+                          const void* base, void* out, void* stream);
+
+/* ---- fused gather + MLP + LayerNorm + residual ("MLP tile") -----------------------------------
+ * One call = one edge update (src/migration/graphnet.py:22-32) or one node update
+ * (graphnet.py:34-48, 94-108, 110-124; heterographnet.py:17-33):
+ *     x_row   = [ chunk_0[row] | chunk_1[row] | ... ]          each chunk 128 wide; chunk_c[row] =
+ *               src_c[idx_c[row]] when idx_c != NULL (gathered sender / receiver latents) else
+ *               src_c[row + row_offset_c]
+ *     out_row = resid[row] + LayerNorm(W2 relu(W1 relu(W0 x + b0) + b1) + b2) * gamma + beta
+ * The concatenation is never materialised (it replaces index_select x2 + cat + 3 addmm + 2 relu +
+ * layer_norm + add = 9 launches).  Weights are the reference's nn.Linear tensors: W0[128, 128*n_chunks],
+ * W1[128,128], W2[128,128] row-major fp32, biases/gamma/beta fp32[128] (meshgraphnet.py:53-60,93-108);
+ * hgn_mlp_pack converts them once per optimiser step into the layout/precision the kernels stage. */
+typedef struct {
+  int32_t n_chunks;
+  const void* src[HGN_MAX_CHUNKS];       /* [*,128] rows of dtype */
+  const int32_t* idx[HGN_MAX_CHUNKS];    /* [rows] gather indices or NULL */
+  int64_t row_offset[HGN_MAX_CHUNKS];    /* used when idx == NULL */
+} hgn_chunks;
+
+size_t hgn_mlp_packed_bytes(int dtype, int32_t n_chunks);
+int hgn_mlp_pack(int dtype, int32_t n_chunks,
+                 const float* W0, const float* b0, const float* W1, const float* b1,
+                 const float* W2, const float* b2, const float* gamma, const float* beta,
+                 void* packed, void* stream);
+
+/* resid may alias one of the chunk sources (edge update: the edge latents; node update: the node
+ * latents); out[rows,128] must not alias any input. */
+int hgn_mlp_forward(int dtype, int64_t rows, const hgn_chunks* chunks, const void* packed,
+                    const void* resid, int64_t resid_row_offset, void* out, void* stream);
+
+/* Backward.  Activations are recomputed from the inputs (nothing but the inputs is saved by the
+ * forward).  Outputs:
+ *   grad_chunk[c][rows,128] : d loss / d chunk_c rows (before the scatter back through idx_c);
+ *                             NULL = not needed.  resid_chunk >= 0 additionally adds grad_out (the
+ *                             gradient of the residual branch, graphnet.py:32,48) into
+ *                             grad_chunk[resid_chunk]; -1 leaves it to the caller.
+ *   grad_W0[128,128*n_chunks], grad_b0, grad_W1, grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta :
+ *                             fp32, overwritten (deterministic two-stage reduction over row tiles). */
+size_t hgn_mlp_backward_workspace_bytes(int dtype, int64_t rows, int32_t n_chunks);
+int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunks, const void* packed,
+                     const void* grad_out, int32_t resid_chunk, void* const* grad_chunk,
+                     float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
+                     float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- column sums ------------------------------------------------------------------------------
+ * out[D] (fp32) = sum over rows of x[rows, D]; two-stage fixed-order reduction (LayerNorm beta / bias
+ * gradients).  D must be a multiple of 4 and <= 1024. */
+size_t hgn_colsum_workspace_bytes(int64_t rows, int32_t D);
+int hgn_colsum(int dtype, const void* x, int64_t rows, int32_t D, float* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- halo exchange helpers (edge-cut partitioning) -------------------------------
+ * pack:   dst[i,:] = src[idx[i],:]            boundary rows -> contiguous send buffer
+ * unpack: dst[idx[i],:] = src[i,:]            received ghost rows -> local ghost slots
+ * unpack_add (backward): dst[idx[i],:] += src[i,:], idx unique per call (one peer at a time, peers in
+ *         rank order -> deterministic). */
+int hgn_rows_gather(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst, void* stream);
+int hgn_rows_scatter(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst,
+                     int accumulate, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end path timed by bench.py "e2e") ---------------------
+ * Not part of the reference API; copies pinned host rows to the device and back on `stream`. */
+int hgn_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
+int hgn_copy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGN_B200_H_ */

@@ -1,0 +1,224 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): the CUDA path, called through the Python mirror
+of the reference API and through the raw C ABI, against the committed golden vectors (produced by the
+live reference) and against the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-5 relative, bf16 mode 2e-2 relative, with
+relative error = max|a-b| / max|b| per tensor; index structure bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import hgn_oracle as orc
+from conftest import GOLDEN_DIR, GoldenCase, MODEL_CASES, rel_err
+from hgn_b200 import _cabi, ops, synthetic
+from hgn_b200 import util as hutil
+from hgn_b200.migration.meshgraphnet import MeshGraphNet
+from hgn_b200.plan import segment_plan
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+GRAD_TOL = {"fp32": 5e-5, "bf16": 4e-2}   # gradients pass through 2x the arithmetic of the forward
+
+
+def _build(case, precision):
+    m = MeshGraphNet(3, 128, 2, case.meta["aggregation"], case.meta["steps"], case.meta["architecture"], case.meta["edge_sets"])
+    m.load_state_dict(case.weights())
+    m = m.cuda()
+    m.processor.precision = precision
+    return m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_model_matches_reference_golden(name, precision):
+    case = GoldenCase(name)
+    m = _build(case, precision)
+    g = case.graph(hutil.MultiGraph, hutil.EdgeSet, device="cuda", requires_grad=True)
+    latent_in = m.encoder(g)
+    latent_out = m.processor(latent_in)
+    out = m.decoder(latent_out._replace(node_features=latent_out.node_features[0]))
+    tol = TOL[precision]
+    assert rel_err(out, case.arr("output")) < tol
+    for i, t in enumerate(latent_out.node_features):
+        assert rel_err(t, case.arr(f"proc_node_{i}")) < tol, f"node latents {i}"
+    assert [es.name for es in latent_out.edge_sets] == case.meta["proc_edge_sets"]
+    for es in latent_out.edge_sets:
+        assert rel_err(es.features, case.arr(f"proc_edge_{es.name}")) < tol, es.name
+    coef = synthetic.seeded_tensor("loss_coef", out.shape, 3).cuda()
+    (out * coef).sum().backward()
+    gtol = GRAD_TOL[precision]
+    for i, nf in enumerate(g.node_features):
+        assert rel_err(nf.grad, case.arr(f"grad_node_features_{i}")) < gtol, f"grad node {i}"
+    for es in g.edge_sets:
+        key = f"grad_edge_{es.name}_features"
+        if key in case.z:
+            assert rel_err(es.features.grad, case.arr(key)) < gtol, key
+    params = dict(m.named_parameters())
+    for key, ref in case.meta["grad_proj"].items():
+        gflat = params[key].grad.double().reshape(-1).cpu()
+        norm = ref[-1]
+        assert abs(float(gflat.norm()) - norm) <= gtol * max(norm, 1e-6), key
+        for i, val in enumerate(ref[:-1]):
+            proj = float(torch.dot(gflat, synthetic.seeded_tensor(f"proj{i}:{key}", gflat.shape, 11).double()))
+            assert abs(proj - val) <= gtol * max(norm * np.sqrt(gflat.numel()), 1e-6), (key, i)
+
+
+def test_segment_ops_match_reference_golden():
+    z = np.load(f"{GOLDEN_DIR}/segment_ops.npz")
+    ids = torch.from_numpy(z["ids"])           # CPU ids, like the reference's callers pass them
+    S = int(z["num_segments"])
+    for op in ("sum", "mean", "max", "min", "std"):
+        x = torch.from_numpy(z["data"]).cuda().requires_grad_(True)
+        out = hutil.unsorted_segment_operation(x, ids, S, op)
+        tol = 1e-6 if op != "std" else 1e-5
+        assert torch.allclose(out.cpu(), torch.from_numpy(z[f"out_{op}"]), rtol=tol, atol=tol), op
+        if op in ("max", "min"):
+            assert torch.equal(out.detach().cpu(), torch.from_numpy(z[f"out_{op}"]))
+        if op != "std":
+            (out * torch.from_numpy(z["grad_up"]).cuda()).sum().backward()
+            assert torch.allclose(x.grad.cpu(), torch.from_numpy(z[f"grad_{op}"]), rtol=1e-6, atol=1e-6), op
+        out1 = hutil.unsorted_segment_operation(torch.from_numpy(z["data1"]).cuda(), ids.cuda(), S, op)
+        assert torch.allclose(out1.cpu(), torch.from_numpy(z[f"out1_{op}"]), rtol=tol, atol=tol), op
+    with pytest.raises(Exception, match="Invalid operation type"):
+        hutil.unsorted_segment_operation(torch.zeros(3, 2).cuda(), torch.zeros(3, dtype=torch.int64), 2, "median")
+    with pytest.raises(AssertionError):
+        hutil.unsorted_segment_operation(torch.zeros(3, 2).cuda(), torch.zeros(5, dtype=torch.int64), 2, "sum")
+    with pytest.raises(_cabi.HgnError):      # id outside [0, S)
+        hutil.unsorted_segment_operation(torch.zeros(3, 4).cuda(), torch.tensor([0, 5, 1]).cuda(), 2, "sum")
+
+
+def test_csr_plan_is_stable_and_bit_exact():
+    rng = np.random.default_rng(3)
+    for E, S in ((0, 5), (1, 1), (1000, 37), (9282, 1600), (200000, 3)):
+        ids = torch.from_numpy(rng.integers(0, S, size=E).astype(np.int64))
+        plan = segment_plan(ids.cuda(), S)
+        perm_ref = torch.sort(ids, stable=True).indices.to(torch.int32)
+        rowptr_ref = torch.cat([torch.zeros(1, dtype=torch.int64), torch.bincount(ids, minlength=S).cumsum(0)]).to(torch.int32)
+        assert torch.equal(plan.rowptr.cpu(), rowptr_ref)
+        if E:
+            assert torch.equal(plan.perm.cpu()[:E], perm_ref)
+            assert torch.equal(plan.ids32.cpu()[:E], ids.to(torch.int32))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_segment_kernels_vs_oracle_ragged(dtype):
+    """Ragged / empty / extreme fan-in segments (hyper-node pooling: N edges into a handful of rows)."""
+    rng = np.random.default_rng(11)
+    for E, S, D in ((0, 4, 128), (5000, 1600, 128), (3000, 7, 128), (64, 64, 128), (500, 50, 4), (300, 20, 3)):
+        ids = torch.from_numpy(rng.integers(0, max(S - 1, 1), size=E).astype(np.int64))
+        x_cpu = torch.from_numpy(rng.standard_normal((E, D)).astype(np.float32)).to(dtype).float()
+        x = x_cpu.to(dtype).cuda().requires_grad_(True)
+        plan = segment_plan(ids.cuda(), S)
+        outs = ops.segment_aggregate(x, plan, ("sum", "mean", "max", "min"))
+        xo = x_cpu.clone().requires_grad_(True)
+        refs = [orc.segment_reduce(xo, ids, S, op) for op in ("sum", "mean", "max", "min")]
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        for o, r, op in zip(outs, refs, ("sum", "mean", "max", "min")):
+            if E == 0:
+                assert float(o.abs().max()) == 0.0 if o.numel() else True
+                continue
+            assert rel_err(o.float(), r) < tol, (E, S, D, op)
+            if op in ("max", "min"):
+                assert torch.equal(o.float().cpu(), r.detach())       # selections are exact in any precision
+        if E == 0:
+            continue
+        gs = [torch.from_numpy(rng.standard_normal(tuple(r.shape)).astype(np.float32)) for r in refs]
+        sum(((o.float() * g.cuda()).sum() for o, g in zip(outs, gs))).backward()
+        sum(((r * g).sum() for r, g in zip(refs, gs))).backward()
+        assert rel_err(x.grad.float(), xo.grad) < (1e-5 if dtype == torch.float32 else 2e-2), (E, S, D)
+
+
+def _random_mlp_weights(n_chunks, seed):
+    shapes = synthetic.mlp_shapes("m", 128 * n_chunks)
+    return synthetic.seeded_state_dict(shapes, seed)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,n_nodes", [(1, 5), (63, 40), (64, 64), (129, 33), (1000, 300), (9282, 1600)])
+def test_fused_edge_update_vs_oracle(rows, n_nodes, precision):
+    """Edge update through the C ABI on ragged tile counts (1 row ... 145 tiles), forward and backward."""
+    dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+    rng = np.random.default_rng(rows)
+    w = _random_mlp_weights(3, 5)
+    s = torch.from_numpy(rng.integers(0, n_nodes, size=rows).astype(np.int64))
+    r = torch.from_numpy(rng.integers(0, n_nodes, size=rows).astype(np.int64))
+    v_cpu = torch.from_numpy(rng.standard_normal((n_nodes, 128)).astype(np.float32)).to(dtype).float()
+    e_cpu = torch.from_numpy(rng.standard_normal((rows, 128)).astype(np.float32)).to(dtype).float()
+    gup = torch.from_numpy(rng.standard_normal((rows, 128)).astype(np.float32)).to(dtype).float()
+    # oracle
+    wo = {f"blk.edge_models.mesh_edges.{k[2:]}": t.clone().requires_grad_(True) for k, t in w.items()}
+    vo, eo = v_cpu.clone().requires_grad_(True), e_cpu.clone().requires_grad_(True)
+    ref = orc.edge_update(wo, "blk", [vo], orc.EdgeSet("mesh_edges", eo, s, r))
+    (ref * gup).sum().backward()
+    # CUDA
+    params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+    params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+    v = v_cpu.to(dtype).cuda().requires_grad_(True)
+    e = e_cpu.to(dtype).cuda().requires_grad_(True)
+    sp, rp = segment_plan(s.cuda(), n_nodes), segment_plan(r.cuda(), n_nodes)
+    out = ops.fused_mlp(params, {}, [v, e], [ops.ChunkSpec(0, sp), ops.ChunkSpec(0, rp), ops.ChunkSpec(1)], rows, resid_source=1)
+    (out.float() * gup.cuda()).sum().backward()
+    tol, gtol = TOL[precision], GRAD_TOL[precision]
+    assert rel_err(out.float(), ref) < tol
+    assert rel_err(e.grad.float(), eo.grad) < gtol
+    assert rel_err(v.grad.float(), vo.grad) < gtol
+    names = [f"blk.edge_models.mesh_edges.0.layers.linear_{k}.{p}" for k in range(3) for p in ("weight", "bias")]
+    names += ["blk.edge_models.mesh_edges.1.weight", "blk.edge_models.mesh_edges.1.bias"]
+    for p, nm in zip(params, names):
+        assert rel_err(p.grad, wo[nm].grad) < gtol, nm
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_processor_vs_oracle_flag_shape(precision):
+    """40x40 cloth (N=1600, E=9282), 3 layers, pna: whole-processor parity against the CPU oracle."""
+    s, r = synthetic.grid_edges_two_way(40, 40)
+    n, E = 1600, s.numel()
+    shapes = synthetic.processor_shapes(3, ["mesh_edges"], "pna")
+    w = synthetic.seeded_state_dict(shapes, 21)
+    v0 = synthetic.seeded_tensor("v0", (n, 128), 1)
+    e0 = synthetic.seeded_tensor("e0", (E, 128), 1)
+    ref = orc.processor(w, "pna", "none", orc.MultiGraph([v0], [orc.EdgeSet("mesh_edges", e0, s, r)]))
+    from hgn_b200.migration.processor import Processor
+    from hgn_b200.migration.graphnet import GraphNet
+    shell = MeshGraphNet(3, 128, 2, "pna", 3, "none", ["mesh_edges"])
+    proc = shell.processor
+    proc.load_state_dict({k[len("processor."):]: t for k, t in w.items()})
+    proc = proc.cuda()
+    proc.precision = precision
+    with torch.no_grad():
+        out = proc(hutil.MultiGraph([v0.cuda()], [hutil.EdgeSet("mesh_edges", e0.cuda(), s, r)]))
+    assert rel_err(out.node_features[0], ref.node_features[0]) < TOL[precision]
+    assert rel_err(out.edge_sets[0].features, ref.edge_sets[0].features) < TOL[precision]
+
+
+def test_fp32_results_are_deterministic():
+    case = GoldenCase("mgn_pna_L1")
+    m = _build(case, "fp32")
+    outs = []
+    for _ in range(2):
+        m.zero_grad()
+        g = case.graph(hutil.MultiGraph, hutil.EdgeSet, device="cuda", requires_grad=True)
+        out = m(g)
+        out.sum().backward()
+        outs.append((out.detach().clone(), g.node_features[0].grad.clone(),
+                     m.processor.graphnet_blocks[0].edge_models["mesh_edges"][0].layers.linear_0.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)      # no float atomics anywhere: bitwise reproducible
+
+
+def test_rows_gather_scatter_and_colsum():
+    lib = _cabi.load()
+    rng = np.random.default_rng(0)
+    for dtype in (torch.float32, torch.bfloat16):
+        src = torch.from_numpy(rng.standard_normal((500, 128)).astype(np.float32)).to(dtype).cuda()
+        idx = torch.from_numpy(rng.permutation(500)[:77].astype(np.int32)).cuda()
+        dst = torch.empty((77, 128), dtype=dtype, device="cuda")
+        _cabi.check(lib.hgn_rows_gather(_cabi.dtype_code(dtype), src.data_ptr(), idx.data_ptr(), 77, 128, dst.data_ptr(), _cabi.stream_ptr()))
+        assert torch.equal(dst, src[idx.long()])
+        back = torch.zeros_like(src)
+        _cabi.check(lib.hgn_rows_scatter(_cabi.dtype_code(dtype), dst.data_ptr(), idx.data_ptr(), 77, 128, back.data_ptr(), 0, _cabi.stream_ptr()))
+        assert torch.equal(back[idx.long()], dst)
+        cs = ops.colsum(src)
+        assert rel_err(cs, src.float().sum(0)) < 1e-5
