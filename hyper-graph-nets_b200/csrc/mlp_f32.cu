@@ -489,6 +489,15 @@ __global__ void reduce_w0_kernel(const float* __restrict__ partial, int parts, i
   dW0[i] = s;
 }
 
+// partial layout [parts][n_chunks + 2][128][128]: z < n_chunks -> W0 chunk z ; n_chunks -> W1 ; n_chunks + 1 -> W2
+void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks, float* gW0, float* gW1, float* gW2, cudaStream_t st) {
+  const int n_z = n_chunks + 2;
+  const int64_t k0 = int64_t(n_chunks) * kD, blk = int64_t(kD) * kD;
+  reduce_w0_kernel<<<unsigned(ceil_div(kD * k0, 256)), 256, 0, st>>>(partial, parts, n_z, n_chunks, gW0);
+  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks) * blk, parts, int64_t(n_z) * blk, blk, gW1);
+  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks + 1) * blk, parts, int64_t(n_z) * blk, blk, gW2);
+}
+
 struct BwdLayoutF32 {
   int64_t slab_rows, tiles, parts;
   int rows_per_part;
@@ -580,11 +589,7 @@ int mlp_f32_backward(int64_t rows, const hgn_chunks* ch, const void* packed, con
     HGN_LAUNCH_OK("mlp_wgrad_f32");
     if (rows == 0) break;
   }
-  const int64_t k0 = int64_t(nch) * kD;
-  reduce_w0_kernel<<<unsigned(ceil_div(kD * k0, 256)), 256, 0, st>>>(partial, int(L.parts), n_z, nch, gW0);
-  const int64_t blk = int64_t(kD) * kD;
-  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(nch) * blk, int(L.parts), int64_t(n_z) * blk, blk, gW1);
-  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(nch + 1) * blk, int(L.parts), int64_t(n_z) * blk, blk, gW2);
+  launch_reduce_weight_partials(partial, int(L.parts), nch, gW0, gW1, gW2, st);
   reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial, int(L.parts), 3 * kD, kD, gb0);
   reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial + kD, int(L.parts), 3 * kD, kD, gb1);
   reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial + 2 * kD, int(L.parts), 3 * kD, kD, gb2);

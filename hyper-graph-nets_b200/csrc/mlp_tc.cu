@@ -1,9 +1,773 @@
-// placeholder until the tcgen05 path lands
+// bf16 tcgen05 path of the fused "MLP tile" (HGN_BF16): gather + 3-layer MLP + LayerNorm + residual,
+// its data-gradient pass (activations recomputed) and the weight-gradient GEMMs.
+//
+// Tile kernel (forward / backward share one skeleton; persistent, one CTA per SM, 13 warps):
+//   warps 8-11  producers  : cp.async gather of 128-row x 128-col bf16 chunks (sender rows, receiver
+//                            rows, edge rows / node rows, aggregates) into a 2-stage ring of
+//                            128B-swizzled K-major operand panels (+ the matching W0 panel pair when
+//                            W0 has more than 3 chunks and is streamed instead of resident)
+//   warp 12     MMA issuer : one thread issues tcgen05.mma (M=128, N=128, K=16, cta_group::1);
+//                            layer 0 = one K=128 accumulation per chunk, so the [rows,128*n] concat
+//                            never exists; every later GEMM takes its A operand (H1, H2, dY, dH2', dH1')
+//                            straight from TMEM; the dgrad GEMMs read the SAME resident weight panels
+//                            as MN-major B operands (no transposed weight copies)
+//   warps 0-3 / 4-7 epilogue groups, one per accumulator slot: tcgen05.ld -> bias + ReLU -> bf16 ->
+//                            tcgen05.st (next A operand); LayerNorm forward/backward are thread-local
+//                            (row = TMEM lane = thread).
+// Two tiles are in flight (TMEM slots 0/1), so the tensor pipe works on one tile while the epilogue
+// warps drain the other.  TMEM: slot s -> accumulator [256s, 256s+128), bf16 A operand [256s+128, +64).
+// Shared memory: W1, W2 (and W0 when <= 3 chunks) resident as SW128 panels; 2 stages.
+//
+// Weight-gradient kernel: dW = G^T Z as tcgen05 GEMMs with BOTH operands MN-major, i.e. the row-major
+// [rows,128] activation / gradient tiles are consumed exactly as they sit in memory; accumulators stay in
+// TMEM over a CTA's whole row range; per-CTA partials are reduced in a fixed order afterwards.
 #include "common.cuh"
+#include "tc05.cuh"
+
 namespace hgn {
-size_t mlp_tc_packed_bytes(int) { return 256; }
-int mlp_tc_pack(int, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, void*, cudaStream_t) { set_error("bf16 path not built"); return HGN_ERR_UNSUPPORTED; }
-int mlp_tc_forward(int64_t, const hgn_chunks*, const void*, const void*, int64_t, void*, cudaStream_t) { set_error("bf16 path not built"); return HGN_ERR_UNSUPPORTED; }
-size_t mlp_tc_backward_workspace_bytes(int64_t, int) { return 256; }
-int mlp_tc_backward(int64_t, const hgn_chunks*, const void*, const void*, int, void* const*, float*, float*, float*, float*, float*, float*, float*, float*, void*, size_t, cudaStream_t) { set_error("bf16 path not built"); return HGN_ERR_UNSUPPORTED; }
+
+using namespace tc05;
+
+constexpr int kTile = 128;                     // rows per tile = TMEM lanes
+constexpr int kPanel = kPanelBytes128;         // 16 KiB: [128][64] bf16
+constexpr int kChunkBytes = 2 * kPanel;        // one 128x128 bf16 operand: 32 KiB
+constexpr int kStages = 2;
+constexpr int kEpiThreads = 256;               // warps 0-7
+constexpr int kProdThreads = 128;              // warps 8-11
+constexpr int kTileThreads = kEpiThreads + kProdThreads + 32;
+constexpr int kMaxResidentChunks = 3;
+constexpr float kEps = 1e-5f;
+
+// fixed-order reductions of the per-CTA weight-gradient partials (defined in mlp_f32.cu)
+void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks, float* gW0, float* gW1, float* gW2, cudaStream_t st);
+
+struct PackedTc {   // byte offsets inside the packed blob
+  size_t w0, w1, w2, params, total;   // params: b0 b1 b2 gamma beta (fp32 x 128 each)
+  __host__ __device__ explicit PackedTc(int n_chunks) {
+    size_t o = 0;
+    w0 = o; o += size_t(n_chunks) * kD * kD * 2;
+    w1 = o; o += size_t(kD) * kD * 2;
+    w2 = o; o += size_t(kD) * kD * 2;
+    params = o; o += 5 * kD * 4;
+    total = o;
+  }
+};
+
+__global__ void pack_tc_kernel(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                               const float* b2, const float* gamma, const float* beta, uint8_t* packed) {
+  const PackedTc L(n_chunks);
+  const int64_t k0 = int64_t(n_chunks) * kD;
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(packed + L.w0);
+  __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(packed + L.w1);
+  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(packed + L.w2);
+  float* p = reinterpret_cast<float*>(packed + L.params);
+  if (i < k0 * kD) w0[i] = __float2bfloat16_rn(W0[i]);
+  if (i < kD * kD) { w1[i] = __float2bfloat16_rn(W1[i]); w2[i] = __float2bfloat16_rn(W2[i]); }
+  if (i < kD) { p[i] = b0[i]; p[kD + i] = b1[i]; p[2 * kD + i] = b2[i]; p[3 * kD + i] = gamma[i]; p[4 * kD + i] = beta[i]; }
 }
+
+// ---- shared-memory map of the tile kernel ------------------------------------------------------------
+struct TileSmem {
+  int w0_panels;          // 2*n_chunks when resident else 0
+  uint32_t w0, w1, w2, stages, params, bars, total;
+  int stage_bytes;
+  __host__ __device__ TileSmem(int n_chunks, bool resident) {
+    w0_panels = resident ? 2 * n_chunks : 0;
+    stage_bytes = resident ? kChunkBytes : 2 * kChunkBytes;
+    uint32_t o = 0;
+    w0 = o; o += uint32_t(w0_panels) * kPanel;
+    w1 = o; o += 2 * kPanel;
+    w2 = o; o += 2 * kPanel;
+    stages = o; o += uint32_t(kStages) * stage_bytes;
+    params = o; o += 5 * kD * 4;
+    bars = o; o += 128;
+    total = o;
+  }
+};
+enum { kBarFull = 0, kBarEmpty = 2, kBarAccFull = 4, kBarEpiDone = 6, kBarTmemPtr = 8 };
+
+// copy a [128][128] bf16 row-major block (row pitch `ld` elements) into two SW128 panels
+__device__ __forceinline__ void load_weight_block(uint32_t smem_dst, const __nv_bfloat16* __restrict__ g, int64_t ld, int tid, int nthreads) {
+  for (int q = tid; q < kTile * 16; q += nthreads) {
+    const int row = q >> 4, c16 = q & 15;
+    cp_async16(smem_dst + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), g + int64_t(row) * ld + c16 * 8);
+  }
+}
+
+struct BwdArgs {
+  const __nv_bfloat16* grad_out;
+  __nv_bfloat16* grad_chunk[HGN_MAX_CHUNKS];
+  __nv_bfloat16 *H1, *H2, *P, *G2, *G1, *G0;   // slab workspaces [rows,128]
+  int resid_chunk;
+};
+
+// 8 MMAs: acc (+)= A[128 x 128] * B^T with A in TMEM (bf16 pairs) and B = a resident 128x128 weight block
+//   b_mn = 0: B K-major   (forward:  out[n] = sum_k A[k] W[n][k])
+//   b_mn = 1: B MN-major  (dgrad:    out[n] = sum_k A[k] W[k][n], the same panels read "transposed")
+__device__ __forceinline__ void issue_ts_gemm(uint32_t acc, uint32_t a_tmem, uint32_t b_addr, int b_mn) {
+  const uint32_t idesc = make_idesc_bf16(128, 128, 0, b_mn);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t bd = b_mn ? sdesc_mnmajor(b_addr + ks * 2048, kPanel)
+                             : sdesc_kmajor(b_addr + (ks >> 2) * kPanel + (ks & 3) * 32);
+    mma_ts(acc, a_tmem + ks * 8, bd, idesc, ks != 0);
+  }
+}
+
+// ---- tile kernel ---------------------------------------------------------------------------------------
+// Steps per tile: forward 0:L0 1:L1 2:L2 ; backward adds 3:dH2=dY W2  4:dH1=dH2' W1  5+c: dX_c = dH1' W0[:,c]
+template <bool kBwd>
+__global__ void __launch_bounds__(kTileThreads, 1)
+mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch, const uint8_t* __restrict__ packed,
+                   int w0_resident, const __nv_bfloat16* __restrict__ resid, int64_t resid_off, __nv_bfloat16* __restrict__ out,
+                   BwdArgs bw) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int nch = ch.n_chunks;
+  const TileSmem S(nch, w0_resident != 0);
+  const PackedTc P(nch);
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();   // SW128 atoms need 1024-byte alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
+  float* sparams = reinterpret_cast<float*>(smem + S.params);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t k0 = int64_t(nch) * kD;
+  const int n_steps = kBwd ? 5 + nch : 3;
+
+  // ---- prologue: resident weights, parameters, barriers, TMEM ------------------------------------
+  {
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    if (w0_resident)
+      for (int c = 0; c < nch; ++c) load_weight_block(sbase + S.w0 + c * kChunkBytes, w0g + c * kD, k0, tid, kTileThreads);
+    load_weight_block(sbase + S.w1, reinterpret_cast<const __nv_bfloat16*>(packed + P.w1), kD, tid, kTileThreads);
+    load_weight_block(sbase + S.w2, reinterpret_cast<const __nv_bfloat16*>(packed + P.w2), kD, tid, kTileThreads);
+    cp_async_commit();
+    const float* pg = reinterpret_cast<const float*>(packed + P.params);
+    for (int i = tid; i < 5 * kD; i += kTileThreads) sparams[i] = pg[i];
+    if (tid == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&bars[kBarFull + s], kProdThreads / kStages); mbar_init(&bars[kBarEmpty + s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars[kBarAccFull + s], 1); mbar_init(&bars[kBarEpiDone + s], kEpiThreads / 2); }
+      mbar_init_fence();
+    }
+    if (warp == 12) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[kBarTmemPtr]));
+    cp_async_wait<0>();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars[kBarTmemPtr]);
+  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles b, b+G, ...
+  const bool stream_w0_bwd = kBwd && !w0_resident;   // dX GEMMs need the W0 panels again
+
+  if (warp >= 8 && warp < 12) {
+    // =============================== producers ====================================================
+    const int ptid = tid - kEpiThreads;          // 0..127
+    const int group = ptid >> 6;                 // 0/1: owns stage `group`
+    const int gt = ptid & 63;
+    if (gt == 0) mbar_arrive(&bars[kBarEmpty + group]);   // the ring starts empty
+    const uint32_t stage_addr = sbase + S.stages + group * S.stage_bytes;
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    int64_t g = 0;                               // running ring-slot counter of this CTA
+    // one ring slot: chunk c of tile `row0` (A operand, when with_a) plus its W0 panel pair (when streamed)
+    auto produce = [&](int64_t row0, int c, bool with_a) {
+      if ((g & 1) == group) {
+        mbar_wait(&bars[kBarEmpty + group], uint32_t(g >> 1) & 1);
+        if (with_a) {
+          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(ch.src[c]);
+          const int32_t* idx = ch.idx[c];
+          const int64_t roff = ch.row_offset[c];
+#pragma unroll 4
+          for (int j = 0; j < 32; ++j) {
+            const int q = gt + 64 * j;             // 2048 16-byte pieces: row = q/16, piece = q%16
+            const int row = q >> 4, c16 = q & 15;
+            const int64_t grow = row0 + row;
+            const bool valid = grow < rows;
+            int64_t srow = 0;
+            if (valid) srow = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
+            cp_async16_zfill(stage_addr + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), src + srow * kD + c16 * 8, valid);
+          }
+        }
+        if (!w0_resident) load_weight_block(stage_addr + kChunkBytes, w0g + c * kD, k0, gt, 64);
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_async_smem();
+        mbar_arrive(&bars[kBarFull + group]);
+      }
+      ++g;
+    };
+    for (int64_t it0 = 0; it0 < my_tiles; it0 += 2) {
+      const int n_in_pair = (it0 + 1 < my_tiles) ? 2 : 1;
+      // layer-0 operands in the MMA issuer's order: tile slot 0 chunk by chunk, then slot 1
+      for (int slot = 0; slot < n_in_pair; ++slot)
+        for (int c = 0; c < nch; ++c) produce(slab0 + (blockIdx.x + (it0 + slot) * gridDim.x) * kTile, c, true);
+      // backward with a streamed W0: the dX GEMMs run chunk-major over the pair
+      if (stream_w0_bwd)
+        for (int c = 0; c < nch; ++c)
+          for (int slot = 0; slot < n_in_pair; ++slot) produce(0, c, false);
+    }
+  } else if (warp == 12) {
+    // =============================== MMA issuer ===================================================
+    if (lane == 0) {
+      const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);
+      int64_t g = 0;
+      uint32_t epi_waits[2] = {0, 0};
+      for (int64_t it0 = 0; it0 < my_tiles; it0 += 2) {
+        const int n_in_pair = (it0 + 1 < my_tiles) ? 2 : 1;
+        for (int step = 0; step < n_steps; ++step) {
+          for (int slot = 0; slot < n_in_pair; ++slot) {
+            const uint32_t acc = tmem_base + slot * 256;
+            const uint32_t aop = acc + 128;
+            // step 0: previous tile's accumulator drained; later steps: A operand written by the epilogue
+            mbar_wait(&bars[kBarEpiDone + slot], epi_waits[slot] & 1);
+            ++epi_waits[slot];
+            fence_after_sync();
+            if (step == 0) {
+              for (int c = 0; c < nch; ++c, ++g) {
+                const int stage = int(g & 1);
+                mbar_wait(&bars[kBarFull + stage], uint32_t(g >> 1) & 1);
+                fence_after_sync();
+                const uint32_t a_addr = sbase + S.stages + stage * S.stage_bytes;
+                const uint32_t b_addr = w0_resident ? sbase + S.w0 + c * kChunkBytes : a_addr + kChunkBytes;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                  const uint32_t koff = (ks >> 2) * kPanel + (ks & 3) * 32;
+                  mma_ss(acc, sdesc_kmajor(a_addr + koff), sdesc_kmajor(b_addr + koff), idesc_kk, (c | ks) != 0);
+                }
+                mma_commit(&bars[kBarEmpty + stage]);
+              }
+            } else if (step == 1) {
+              issue_ts_gemm(acc, aop, sbase + S.w1, 0);
+            } else if (step == 2) {
+              issue_ts_gemm(acc, aop, sbase + S.w2, 0);
+            } else if (step == 3) {
+              issue_ts_gemm(acc, aop, sbase + S.w2, 1);
+            } else if (step == 4) {
+              issue_ts_gemm(acc, aop, sbase + S.w1, 1);
+            } else {
+              const int c = step - 5;
+              if (w0_resident) {
+                issue_ts_gemm(acc, aop, sbase + S.w0 + c * kChunkBytes, 1);
+              } else {
+                // W0 panels stream through the ring again, chunk-major over the pair like the producers walk it
+                const int64_t gg = g + int64_t(c) * n_in_pair + slot;
+                const int stage = int(gg & 1);
+                mbar_wait(&bars[kBarFull + stage], uint32_t(gg >> 1) & 1);
+                fence_after_sync();
+                issue_ts_gemm(acc, aop, sbase + S.stages + stage * S.stage_bytes + kChunkBytes, 1);
+                mma_commit(&bars[kBarEmpty + stage]);
+              }
+            }
+            mma_commit(&bars[kBarAccFull + slot]);
+          }
+        }
+        if (stream_w0_bwd) g += int64_t(n_in_pair) * nch;
+      }
+    }
+  } else {
+    // =============================== epilogue groups ==============================================
+    const int slot = warp >> 2;                       // warps 0-3 -> slot 0, warps 4-7 -> slot 1
+    const int r = (warp & 3) * 32 + lane;             // tile row = TMEM lane
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t acc = tmem_base + slot * 256 + lane_addr;
+    const uint32_t aop = acc + 128;
+    mbar_arrive(&bars[kBarEpiDone + slot]);           // accumulator slot starts free
+    uint32_t acc_waits = 0;
+    auto wait_acc = [&]() {
+      mbar_wait(&bars[kBarAccFull + slot], acc_waits & 1);
+      ++acc_waits;
+      fence_after_sync();
+    };
+    auto signal_done = [&]() {
+      fence_before_sync();
+      mbar_arrive(&bars[kBarEpiDone + slot]);
+    };
+    const float* b2 = sparams + 2 * kD;
+    const float* gam = sparams + 3 * kD;
+    const float* bet = sparams + 4 * kD;
+    for (int64_t it = slot; it < my_tiles; it += 2) {
+      const int64_t grow = slab0 + (blockIdx.x + it * gridDim.x) * kTile + r;
+      const bool valid = grow < rows;
+      const int64_t lrow = valid ? grow - slab0 : 0;   // row inside the slab workspaces
+      uint32_t mask1[4] = {0, 0, 0, 0}, mask2[4] = {0, 0, 0, 0};   // ReLU masks (backward)
+      // ---- hidden layers: bias + ReLU -> bf16 A operand in TMEM -------------------------------
+      for (int layer = 0; layer < 2; ++layer) {
+        wait_acc();
+        const float* bias = sparams + layer * kD;
+        uint4* hws = kBwd ? reinterpret_cast<uint4*>((layer == 0 ? bw.H1 : bw.H2) + lrow * kD) : nullptr;
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          uint32_t h[16];
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaxf(__uint_as_float(v[2 * j]) + bias[cg * 32 + 2 * j], 0.f);
+            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[cg * 32 + 2 * j + 1], 0.f);
+            h[j] = pack_bf16(a, b);
+            if (kBwd) m |= (a > 0.f ? (1u << (2 * j)) : 0u) | (b > 0.f ? (1u << (2 * j + 1)) : 0u);
+          }
+          tmem_st8(aop + cg * 16, h);
+          tmem_st8(aop + cg * 16 + 8, h + 8);
+          if (kBwd) {
+            if (layer == 0) mask1[cg] = m; else mask2[cg] = m;
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) hws[cg * 4 + q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            }
+          }
+        }
+        tmem_st_wait();
+        signal_done();
+      }
+      // ---- last layer: bias, LayerNorm statistics -----------------------------------------------
+      wait_acc();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(acc + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + b2[cg * 32 + j];
+      }
+      const float mean = sum * (1.0f / kD);
+      float sq = 0.f;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(acc + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(v[j]) + b2[cg * 32 + j] - mean; sq = fmaf(d, d, sq); }
+      }
+      const float rstd = rsqrtf(sq * (1.0f / kD) + kEps);
+      if (!kBwd) {
+        // ---- forward: affine, residual, store -------------------------------------------------
+        const uint4* rp = reinterpret_cast<const uint4*>(resid + (valid ? grow + resid_off : 0) * kD);
+        uint4* op = reinterpret_cast<uint4*>(out + (valid ? grow : 0) * kD);
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(rp + cg * 4 + q);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int col = cg * 32 + q * 8 + t * 2;
+                const float y0 = (__uint_as_float(v[q * 8 + t * 2]) + b2[col] - mean) * rstd * gam[col] + bet[col];
+                const float y1 = (__uint_as_float(v[q * 8 + t * 2 + 1]) + b2[col + 1] - mean) * rstd * gam[col + 1] + bet[col + 1];
+                ow[t] = pack_bf16(bf16_lo(rw[t]) + y0, bf16_hi(rw[t]) + y1);
+              }
+              op[cg * 4 + q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+        }
+        signal_done();
+      } else {
+        // ---- backward: LayerNorm backward -> dY (A operand) ; P = dO * yhat for the gamma gradient --
+        const uint4* gop = reinterpret_cast<const uint4*>(bw.grad_out + (valid ? grow : 0) * kD);
+        uint4* pws = reinterpret_cast<uint4*>(bw.P + lrow * kD);
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          uint32_t dpk[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 gv = make_uint4(0, 0, 0, 0);
+            if (valid) gv = __ldg(gop + cg * 4 + q);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+            uint32_t pw[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = cg * 32 + q * 8 + t * 2;
+              const float yh0 = (__uint_as_float(v[q * 8 + t * 2]) + b2[col] - mean) * rstd;
+              const float yh1 = (__uint_as_float(v[q * 8 + t * 2 + 1]) + b2[col + 1] - mean) * rstd;
+              const float d0 = bf16_lo(gw[t]), d1 = bf16_hi(gw[t]);
+              const float dy0 = d0 * gam[col], dy1 = d1 * gam[col + 1];
+              m1 += dy0 + dy1;
+              m2 = fmaf(dy0, yh0, fmaf(dy1, yh1, m2));
+              pw[t] = pack_bf16(d0 * yh0, d1 * yh1);
+              dpk[q * 4 + t] = gw[t];
+            }
+            if (valid) pws[cg * 4 + q] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          }
+          tmem_st8(aop + cg * 16, dpk);          // park dO (bf16) in the free A-operand columns
+          tmem_st8(aop + cg * 16 + 8, dpk + 8);
+        }
+        tmem_st_wait();
+        m1 *= (1.0f / kD);
+        m2 *= (1.0f / kD);
+        uint4* g2ws = reinterpret_cast<uint4*>(bw.G2 + lrow * kD);
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32], dpk[16];
+          tmem_ld32(acc + cg * 32, v);
+          // 16 packed dO words of this column group
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(dpk[0]), "=r"(dpk[1]), "=r"(dpk[2]), "=r"(dpk[3]), "=r"(dpk[4]), "=r"(dpk[5]), "=r"(dpk[6]), "=r"(dpk[7]),
+                         "=r"(dpk[8]), "=r"(dpk[9]), "=r"(dpk[10]), "=r"(dpk[11]), "=r"(dpk[12]), "=r"(dpk[13]), "=r"(dpk[14]), "=r"(dpk[15])
+                       : "r"(aop + cg * 16) : "memory");
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cg * 32 + 2 * j;
+            const float yh0 = (__uint_as_float(v[2 * j]) + b2[col] - mean) * rstd;
+            const float yh1 = (__uint_as_float(v[2 * j + 1]) + b2[col + 1] - mean) * rstd;
+            const float dy0 = rstd * (bf16_lo(dpk[j]) * gam[col] - m1 - yh0 * m2);
+            const float dy1 = rstd * (bf16_hi(dpk[j]) * gam[col + 1] - m1 - yh1 * m2);
+            o[j] = pack_bf16(dy0, dy1);
+          }
+          tmem_st8(aop + cg * 16, o);
+          tmem_st8(aop + cg * 16 + 8, o + 8);
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g2ws[cg * 4 + q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          }
+        }
+        tmem_st_wait();
+        signal_done();
+        // ---- dH2' = (dY W2) * [H2 > 0] ; dH1' = (dH2' W1) * [H1 > 0] ------------------------------
+        for (int layer = 1; layer >= 0; --layer) {
+          wait_acc();
+          uint4* gws = reinterpret_cast<uint4*>((layer == 1 ? bw.G1 : bw.G0) + lrow * kD);
+#pragma unroll 1
+          for (int cg = 0; cg < 4; ++cg) {
+            uint32_t v[32];
+            tmem_ld32(acc + cg * 32, v);
+            tmem_ld_wait();
+            const uint32_t m = layer == 1 ? mask2[cg] : mask1[cg];
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = (m >> (2 * j)) & 1u ? __uint_as_float(v[2 * j]) : 0.f;
+              const float b = (m >> (2 * j + 1)) & 1u ? __uint_as_float(v[2 * j + 1]) : 0.f;
+              o[j] = pack_bf16(a, b);
+            }
+            tmem_st8(aop + cg * 16, o);
+            tmem_st8(aop + cg * 16 + 8, o + 8);
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) gws[cg * 4 + q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            }
+          }
+          tmem_st_wait();
+          signal_done();
+        }
+        // ---- dX_c = dH1' W0[:, c]  (+ grad_out for the residual chunk) -------------------------------
+        for (int c = 0; c < nch; ++c) {
+          wait_acc();
+          __nv_bfloat16* dst = bw.grad_chunk[c];
+          if (dst != nullptr) {
+            uint4* dp = reinterpret_cast<uint4*>(dst + (valid ? grow : 0) * kD);
+            const bool add_resid = (c == bw.resid_chunk);
+#pragma unroll 1
+            for (int cg = 0; cg < 4; ++cg) {
+              uint32_t v[32];
+              tmem_ld32(acc + cg * 32, v);
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 gv = make_uint4(0, 0, 0, 0);
+                  if (add_resid) gv = __ldg(gop + cg * 4 + q);
+                  const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                  uint32_t ow[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    ow[t] = pack_bf16(__uint_as_float(v[q * 8 + t * 2]) + bf16_lo(gw[t]), __uint_as_float(v[q * 8 + t * 2 + 1]) + bf16_hi(gw[t]));
+                  dp[cg * 4 + q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+              }
+            }
+          }
+          signal_done();
+        }
+      }
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------------------
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- weight-gradient kernel --------------------------------------------------------------------------
+// grid (parts, groups).  group 0: dW2 = G2^T H2, dW1 = G1^T H1.  group j >= 1: dW0 chunks 3(j-1) .. 3(j-1)+2
+// = G0^T X_c (X_c gathered like in the forward).  K (= rows) advances in 64-row stages; every operand tile
+// [64 rows][128 cols] bf16 sits in two SW128 panels of 8 KiB and is read MN-major.
+constexpr int kWgRows = 64;
+constexpr int kWgTileBytes = 2 * 8192;         // one [64][128] operand tile
+constexpr int kWgStageTiles = 4;
+constexpr int kWgStageBytes = kWgStageTiles * kWgTileBytes;   // 64 KiB
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 128 + 32 + 128;     // warps 0-3 producers, warp 4 MMA, warps 5-8 epilogue (final drain)
+
+struct WgradArgs {
+  const __nv_bfloat16 *G2, *G1, *G0, *H1, *H2;
+  float* partial;       // [parts][n_z][128][128]
+  int n_z;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows_per_part, hgn_chunks ch, WgradArgs wa) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);   // full[3], empty[3], done, tmem ptr
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int part = blockIdx.x, group = blockIdx.y, nch = ch.n_chunks;
+  const int c_first = group == 0 ? 0 : 3 * (group - 1);
+  const int n_out = group == 0 ? 2 : min(3, nch - c_first);          // accumulators of this CTA
+  const int n_tiles = group == 0 ? 4 : 1 + n_out;                    // operand tiles per stage
+  const int64_t row_end = min(rows, slab0 + slab_rows);
+  const int64_t r_beg = slab0 + int64_t(part) * rows_per_part;
+  const int64_t r_end = min(row_end, r_beg + rows_per_part);
+  const int64_t n_steps = r_end > r_beg ? (r_end - r_beg + kWgRows - 1) / kWgRows : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bars[s], 128); mbar_init(&bars[3 + s], 1); }
+    mbar_init(&bars[6], 1);
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[7]));
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars[7]);
+
+  if (warp < 4) {
+    // ---- producers: dense rows (and gathered X chunks) -> MN-major operand tiles ------------------------
+    if (tid < kWgStages) mbar_arrive(&bars[3 + tid]);     // ring starts empty
+    for (int64_t st = 0; st < n_steps; ++st) {
+      const int stage = int(st % kWgStages);
+      mbar_wait(&bars[3 + stage], uint32_t(st / kWgStages) & 1);
+      const int64_t row0 = r_beg + st * kWgRows;
+      const uint32_t saddr = sbase + stage * kWgStageBytes;
+      for (int t = 0; t < n_tiles; ++t) {
+        const __nv_bfloat16* src;
+        const int32_t* idx = nullptr;
+        int64_t roff = -slab0;                 // workspace tiles are slab-local
+        if (group == 0) src = t == 0 ? wa.G2 : t == 1 ? wa.H2 : t == 2 ? wa.G1 : wa.H1;
+        else if (t == 0) src = wa.G0;
+        else { src = static_cast<const __nv_bfloat16*>(ch.src[c_first + t - 1]); idx = ch.idx[c_first + t - 1]; roff = ch.row_offset[c_first + t - 1]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = tid + 128 * j;           // 1024 16-byte pieces
+          const int row = q >> 4, c16 = q & 15;
+          const int64_t grow = row0 + row;
+          const bool valid = grow < r_end;
+          int64_t srow = 0;
+          if (valid) srow = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
+          cp_async16_zfill(saddr + t * kWgTileBytes + (c16 >> 3) * 8192 + sw128_chunk(row, c16 & 7), src + srow * kD + c16 * 8, valid);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_async_smem();
+      mbar_arrive(&bars[stage]);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);     // both operands MN-major
+      for (int64_t st = 0; st < n_steps; ++st) {
+        const int stage = int(st % kWgStages);
+        mbar_wait(&bars[stage], uint32_t(st / kWgStages) & 1);
+        fence_after_sync();
+        const uint32_t saddr = sbase + stage * kWgStageBytes;
+        for (int o = 0; o < n_out; ++o) {
+          const uint32_t a_addr = saddr + (group == 0 ? 2 * o : 0) * kWgTileBytes;            // G tile
+          const uint32_t b_addr = saddr + (group == 0 ? 2 * o + 1 : 1 + o) * kWgTileBytes;    // Z tile
+#pragma unroll
+          for (int ks = 0; ks < kWgRows / 16; ++ks)
+            mma_ss(tmem_base + o * 128, sdesc_mnmajor(a_addr + ks * 2048, 8192), sdesc_mnmajor(b_addr + ks * 2048, 8192), idesc,
+                   (st | ks) != 0);
+        }
+        mma_commit(&bars[3 + stage]);
+      }
+      mma_commit(&bars[6]);
+    }
+  } else {
+    // ---- final drain: TMEM accumulators -> fp32 partials ---------------------------------------------------
+    const int ew = warp - 5;                      // 0..3
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    (void)ew;
+    if (n_steps > 0) {
+      mbar_wait(&bars[6], 0);
+      fence_after_sync();
+    }
+    const int o_row = quarter * 32 + lane;        // output row (= "out" feature of the weight)
+    for (int o = 0; o < n_out; ++o) {
+      const int z = group == 0 ? (o == 0 ? nch + 1 : nch) : c_first + o;     // partial layout: W0 chunks, W1, W2
+      float* dst = wa.partial + ((int64_t(part) * wa.n_z + z) * kD + o_row) * kD;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t v[32];
+        if (n_steps > 0) {
+          tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + o * 128 + cg * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 val = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          float4* p = reinterpret_cast<float4*>(dst + cg * 32 + q * 4);
+          if (wa.accumulate) { const float4 old = *p; val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w; }
+          *p = val;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+size_t mlp_tc_packed_bytes(int n_chunks) { return PackedTc(n_chunks).total; }
+
+int mlp_tc_pack(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                const float* b2, const float* gamma, const float* beta, void* packed, cudaStream_t st) {
+  const int64_t n = int64_t(n_chunks) * kD * kD;
+  pack_tc_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(n_chunks, W0, b0, W1, b1, W2, b2, gamma, beta, static_cast<uint8_t*>(packed));
+  HGN_LAUNCH_OK("pack_tc");
+  return HGN_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int configure_kernels() {
+  static bool configured = false;
+  if (!configured) {
+    HGN_CUDA_OK(cudaFuncSetAttribute(mlp_tile_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    HGN_CUDA_OK(cudaFuncSetAttribute(mlp_tile_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    HGN_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  return HGN_OK;
+}
+
+int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
+                   cudaStream_t st) {
+  const int nch = ch->n_chunks;
+  const bool resident = nch <= kMaxResidentChunks;
+  const TileSmem S(nch, resident);
+  if (int rc = configure_kernels()) return rc;
+  const int64_t tiles = ceil_div(rows, kTile);
+  const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
+  BwdArgs none{};
+  mlp_tile_tc_kernel<false><<<grid, kTileThreads, S.total, st>>>(rows, tiles, 0, *ch, static_cast<const uint8_t*>(packed), resident ? 1 : 0,
+                                                                 static_cast<const __nv_bfloat16*>(resid), resid_off,
+                                                                 static_cast<__nv_bfloat16*>(out), none);
+  HGN_LAUNCH_OK("mlp_fwd_tc");
+  return HGN_OK;
+}
+
+struct BwdLayoutTc {
+  int64_t slab_rows, parts, rows_per_part;
+  int groups, n_z;
+  size_t act[6], partial, vec_partial, total;   // act: H1 H2 P G2 G1 G0
+};
+
+static BwdLayoutTc bwd_layout_tc(int64_t rows, int n_chunks) {
+  BwdLayoutTc L{};
+  const int64_t cap = int64_t(1) << 21;                      // <= 2M rows per pass (6 x 512 MiB of bf16 workspace)
+  L.slab_rows = rows < cap ? (rows > 0 ? rows : 1) : cap;
+  L.slab_rows = ceil_div(L.slab_rows, kTile) * kTile;
+  L.parts = L.slab_rows >= int64_t(sm_count()) * 4 * kWgRows ? sm_count() : ceil_div(L.slab_rows, 4 * kWgRows);
+  L.rows_per_part = ceil_div(ceil_div(L.slab_rows, L.parts), kWgRows) * kWgRows;
+  L.groups = 1 + (n_chunks + 2) / 3;
+  L.n_z = n_chunks + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  for (int i = 0; i < 6; ++i) L.act[i] = take(size_t(L.slab_rows) * kD * 2);
+  L.partial = take(size_t(L.parts) * L.n_z * kD * kD * 4);
+  L.vec_partial = take(size_t(ceil_div(L.slab_rows, 2048)) * kD * 4 + 5 * kD * 4 * 2);
+  L.total = off;
+  return L;
+}
+
+size_t mlp_tc_backward_workspace_bytes(int64_t rows, int n_chunks) { return bwd_layout_tc(rows, n_chunks).total; }
+
+__global__ void axpy_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = accumulate ? dst[i] + src[i] : src[i];
+}
+
+int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* grad_out, int resid_chunk,
+                    void* const* grad_chunk, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2,
+                    float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int nch = ch->n_chunks;
+  const bool resident = nch <= kMaxResidentChunks;
+  const TileSmem S(nch, resident);
+  const BwdLayoutTc L = bwd_layout_tc(rows, nch);
+  if (workspace_bytes < L.total) { set_error("mlp_backward(bf16): workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  if (int rc = configure_kernels()) return rc;
+  char* ws = static_cast<char*>(workspace);
+  BwdArgs bw{};
+  bw.grad_out = static_cast<const __nv_bfloat16*>(grad_out);
+  for (int c = 0; c < nch; ++c) bw.grad_chunk[c] = grad_chunk ? static_cast<__nv_bfloat16*>(grad_chunk[c]) : nullptr;
+  bw.H1 = (__nv_bfloat16*)(ws + L.act[0]); bw.H2 = (__nv_bfloat16*)(ws + L.act[1]); bw.P = (__nv_bfloat16*)(ws + L.act[2]);
+  bw.G2 = (__nv_bfloat16*)(ws + L.act[3]); bw.G1 = (__nv_bfloat16*)(ws + L.act[4]); bw.G0 = (__nv_bfloat16*)(ws + L.act[5]);
+  bw.resid_chunk = resid_chunk;
+  float* partial = (float*)(ws + L.partial);
+  float* vec_ws = (float*)(ws + L.vec_partial);
+  float* vec_tmp = vec_ws + ceil_div(L.slab_rows, 2048) * kD;   // 5 x 128 staging for per-slab column sums
+  const size_t colsum_ws_bytes = size_t(ceil_div(L.slab_rows, 2048)) * kD * 4;
+  WgradArgs wa{};
+  wa.G2 = bw.G2; wa.G1 = bw.G1; wa.G0 = bw.G0; wa.H1 = bw.H1; wa.H2 = bw.H2;
+  wa.partial = partial; wa.n_z = L.n_z;
+  const size_t wg_smem = size_t(kWgStages) * kWgStageBytes + 64;
+  float* vec_out[5] = {gb2, gb1, gb0, ggamma, gbeta};
+  int pass = 0;
+  for (int64_t slab0 = 0; slab0 < rows || pass == 0; slab0 += L.slab_rows, ++pass) {
+    const int64_t this_rows = rows - slab0 < L.slab_rows ? rows - slab0 : L.slab_rows;
+    if (this_rows > 0) {
+      const int64_t tiles = ceil_div(this_rows, kTile);
+      const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
+      mlp_tile_tc_kernel<true><<<grid, kTileThreads, S.total, st>>>(rows, tiles, slab0, *ch, static_cast<const uint8_t*>(packed),
+                                                                    resident ? 1 : 0, nullptr, 0, nullptr, bw);
+      HGN_LAUNCH_OK("mlp_bwd_tc");
+    }
+    wa.accumulate = pass > 0;
+    dim3 grid(unsigned(L.parts), unsigned(L.groups));
+    mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(rows, slab0, L.slab_rows, L.rows_per_part, *ch, wa);
+    HGN_LAUNCH_OK("mlp_wgrad_tc");
+    // bias / LayerNorm vector gradients: column sums of G2, G1, G0, P and grad_out over this slab
+    const void* mats[5] = {bw.G2, bw.G1, bw.G0, bw.P, bw.grad_out ? (const void*)(bw.grad_out + slab0 * kD) : nullptr};
+    for (int i = 0; i < 5; ++i) {
+      float* dst = pass == 0 ? vec_out[i] : vec_tmp + i * kD;
+      if (int rc = hgn_colsum(HGN_BF16, mats[i], this_rows > 0 ? this_rows : 0, kD, dst, vec_ws, colsum_ws_bytes, st)) return rc;
+      if (pass > 0) axpy_vec_kernel<<<1, 128, 0, st>>>(vec_out[i], dst, kD, 1);
+    }
+    if (rows == 0) break;
+  }
+  launch_reduce_weight_partials(partial, int(L.parts), nch, gW0, gW1, gW2, st);
+  HGN_LAUNCH_OK("mlp_bwd_tc reductions");
+  return HGN_OK;
+}
+
+}  // namespace hgn

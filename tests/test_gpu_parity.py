@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import hgn_oracle as orc
-from conftest import GOLDEN_DIR, GoldenCase, MODEL_CASES, rel_err
+from conftest import GOLDEN_DIR, GoldenCase, MODEL_CASES, rel_err, rel_l2
 from hgn_b200 import _cabi, ops, synthetic
 from hgn_b200 import util as hutil
 from hgn_b200.migration.meshgraphnet import MeshGraphNet
@@ -19,7 +19,16 @@ from hgn_b200.plan import segment_plan
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-5, "bf16": 2e-2}
-GRAD_TOL = {"fp32": 5e-5, "bf16": 4e-2}   # gradients pass through 2x the arithmetic of the forward
+# fp32: max metric.  bf16: L2 metric against the FP32 reference; the bound is loose on purpose -- with ~0.3% of
+# the ReLU pre-activations inside bf16 rounding noise of zero, about half of all rows have one of their ~64 active
+# hidden units switched relative to fp32, which moves that row's data gradient by ~1/sqrt(64) (measured 0.10-0.16
+# on the goldens).  Kernel correctness of the bf16 backward is pinned separately, at 1e-2, by
+# test_bf16_kernels_vs_bf16_emulation (same rounding points => same ReLU masks).
+GRAD_TOL = {"fp32": 5e-5, "bf16": 3e-1}
+
+
+def grad_err(a, b, precision):
+    return rel_err(a, b) if precision == "fp32" else rel_l2(a, b)
 
 
 def _build(case, precision):
@@ -50,11 +59,11 @@ def test_model_matches_reference_golden(name, precision):
     (out * coef).sum().backward()
     gtol = GRAD_TOL[precision]
     for i, nf in enumerate(g.node_features):
-        assert rel_err(nf.grad, case.arr(f"grad_node_features_{i}")) < gtol, f"grad node {i}"
+        assert grad_err(nf.grad, case.arr(f"grad_node_features_{i}"), precision) < gtol, f"grad node {i}"
     for es in g.edge_sets:
         key = f"grad_edge_{es.name}_features"
         if key in case.z:
-            assert rel_err(es.features.grad, case.arr(key)) < gtol, key
+            assert grad_err(es.features.grad, case.arr(key), precision) < gtol, key
     params = dict(m.named_parameters())
     for key, ref in case.meta["grad_proj"].items():
         gflat = params[key].grad.double().reshape(-1).cpu()
@@ -162,12 +171,12 @@ def test_fused_edge_update_vs_oracle(rows, n_nodes, precision):
     (out.float() * gup.cuda()).sum().backward()
     tol, gtol = TOL[precision], GRAD_TOL[precision]
     assert rel_err(out.float(), ref) < tol
-    assert rel_err(e.grad.float(), eo.grad) < gtol
-    assert rel_err(v.grad.float(), vo.grad) < gtol
+    assert grad_err(e.grad.float(), eo.grad, precision) < gtol
+    assert grad_err(v.grad.float(), vo.grad, precision) < gtol
     names = [f"blk.edge_models.mesh_edges.0.layers.linear_{k}.{p}" for k in range(3) for p in ("weight", "bias")]
     names += ["blk.edge_models.mesh_edges.1.weight", "blk.edge_models.mesh_edges.1.bias"]
     for p, nm in zip(params, names):
-        assert rel_err(p.grad, wo[nm].grad) < gtol, nm
+        assert grad_err(p.grad, wo[nm].grad, precision) < gtol, nm
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -222,3 +231,38 @@ def test_rows_gather_scatter_and_colsum():
         assert torch.equal(back[idx.long()], dst)
         cs = ops.colsum(src)
         assert rel_err(cs, src.float().sum(0)) < 1e-5
+
+
+def _bf16_emulated_mlp(x, w):
+    """torch fp32 arithmetic on bf16-rounded operands, rounding H1/H2 where the kernel does."""
+    W0, b0, W1, b1, W2, b2, g, b = w
+    r = lambda t: t.to(torch.bfloat16).float()
+    h = torch.relu(x @ r(W0).t() + b0)
+    h = torch.relu(r(h) @ r(W1).t() + b1)
+    return torch.nn.functional.layer_norm(r(h) @ r(W2).t() + b2, (128,), g, b, 1e-5)
+
+
+@pytest.mark.parametrize("rows,n_nodes", [(128, 64), (9282, 1600), (200000, 40000)])
+def test_bf16_kernels_vs_bf16_emulation(rows, n_nodes):
+    """The tcgen05 kernels against torch arithmetic with the SAME rounding points: isolates kernel bugs
+    from the bf16-vs-fp32 model difference (forward max metric 1e-2 = bf16 output rounding)."""
+    torch.manual_seed(rows)
+    w = _random_mlp_weights(3, 9)
+    params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+    params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+    s = torch.randint(0, n_nodes, (rows,), device="cuda")
+    r = torch.randint(0, n_nodes, (rows,), device="cuda")
+    v = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    e = torch.randn(rows, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    gup = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
+    sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
+    out = ops.fused_mlp(params, {}, [v, e], [ops.ChunkSpec(0, sp), ops.ChunkSpec(0, rp), ops.ChunkSpec(1)], rows, resid_source=1)
+    out.backward(gup)
+    wr = [p.detach().clone().requires_grad_(True) for p in params]
+    vf, ef = v.detach().float().requires_grad_(True), e.detach().float().requires_grad_(True)
+    ref = ef + _bf16_emulated_mlp(torch.cat([vf[s], vf[r], ef], -1), wr)
+    ref.backward(gup.float())
+    assert rel_err(out.float(), ref) < 1e-2
+    assert rel_l2(e.grad.float(), ef.grad) < 1e-2 and rel_l2(v.grad.float(), vf.grad) < 1e-2
+    for a, b in zip(params, wr):
+        assert rel_l2(a.grad, b.grad) < 1e-2
