@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Headline benchmark: edge-updates/sec per message-passing layer (forward + backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[4], SURVEY.md s8 cfg 5): synthetic 1000 x 1000 triangulated grid,
+N = 1 000 000 nodes, E = 5 992 002 directed mesh edges, latent 128, 15 unshared GraphNet layers, `sum`
+aggregator, processor only (latents in, latents out), bf16 tcgen05 mode.  One step = Processor.forward
++ backward of a seeded linear loss w.r.t. all latents and weights.
+
+value   : E * L / t with the inputs resident in HBM (CUDA events, max over ranks)
+e2e     : the same through the public module API with pinned HOST inputs: H2D copy of the fp32 latents,
+          forward + backward, D2H read of the loss, all inside the timed region
+roofline: the dominant kernel's algorithmic FLOPs per launch / its mean launch time (CUDA events recorded
+          inside the library around every launch during the timed region) against MEASURED_PEAKS.json
+cpu_baseline / --impl reference: the oracle port of the reference's torch path (oracle/hgn_oracle.py)
+          on the host cores, on a bounded sub-mesh of the same workload.
+With --gpus N > 1 (torchrun) the mesh is edge-cut partitioned into N row slabs with a halo exchange of
+boundary node latents per layer (strong scaling: the total mesh is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hyper-graph-nets_b200"))
+
+import torch  # noqa: E402
+
+GRID_W, GRID_H = 1000, 1000
+LAYERS = 15
+LATENT = 128
+METRIC = "edge-updates/sec per MP layer (fwd+bwd)"
+UNIT = "edge-updates/s"
+F_EDGE = 10 * LATENT * LATENT           # GEMM flops per edge, forward
+F_NODE_SUM = 2 * (2 + 2) * LATENT * LATENT
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in self.rows:
+            try:
+                sm.append(float(row[0])); mx.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, row[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+def build_inputs(width, height, layers, seed=0):
+    """Host-side (pinned) latents, int64 edge lists and the seeded processor weights."""
+    from hgn_b200 import synthetic
+    senders, receivers = synthetic.grid_edges_two_way(width, height)
+    n, e = width * height, senders.numel()
+    gen = torch.Generator().manual_seed(seed)
+    v0 = torch.randn(n, LATENT, generator=gen)
+    e0 = torch.randn(e, LATENT, generator=gen)
+    coef_v = torch.randn(n, LATENT, generator=gen)
+    weights = synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), seed=17)
+    return {"senders": senders, "receivers": receivers, "v0": v0, "e0": e0, "coef_v": coef_v, "weights": weights, "n": n, "e": e}
+
+
+def make_processor(weights, layers, precision, device):
+    from hgn_b200.migration.meshgraphnet import MeshGraphNet
+    shell = MeshGraphNet(3, LATENT, 2, "sum", layers, "none", ["mesh_edges"])
+    proc = shell.processor
+    proc.load_state_dict({k[len("processor."):]: t for k, t in weights.items()})
+    proc = proc.to(device)
+    proc.precision = precision
+    return proc
+
+
+def run_ours(args):
+    from hgn_b200 import _cabi, ops
+    from hgn_b200.util import EdgeSet, MultiGraph
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        from hgn_b200 import partition
+        return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler)
+
+    data = build_inputs(GRID_W, GRID_H, LAYERS)
+    n, e = data["n"], data["e"]
+    proc = make_processor(data["weights"], LAYERS, "bf16", dev)
+    params = [p for p in proc.parameters()]
+    senders, receivers = data["senders"].to(dev), data["receivers"].to(dev)
+    v0_host, e0_host = data["v0"].pin_memory(), data["e0"].pin_memory()
+    coef_v = data["coef_v"].to(dev)
+    v_dev = v0_host.to(dev)
+    e_dev = e0_host.to(dev)
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(v_in, e_in):
+        for p in params:
+            p.grad = None
+        v = v_in.requires_grad_(True)
+        ed = e_in.requires_grad_(True)
+        out = proc(MultiGraph([v], [EdgeSet("mesh_edges", ed, senders, receivers)]))
+        loss = (out.node_features[0] * coef_v).sum() + out.edge_sets[0].features.sum() * 1e-3
+        loss.backward()
+        return loss
+
+    def step_resident():
+        return step(v_dev.detach(), e_dev.detach())
+
+    def step_e2e():
+        v = v0_host.to(dev, non_blocking=True)
+        ed = e0_host.to(dev, non_blocking=True)
+        loss = step(v, ed)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss_host
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # ---- timed region: inputs resident in HBM --------------------------------------------------------
+    _cabi.profile(True)
+    launches0 = ops.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            step_resident()
+        stop.record()
+        torch.cuda.synchronize()
+    ms_per_step = start.elapsed_time(stop) / args.steps
+    launches = ops.launch_count - launches0
+    kernels = _cabi.profile_report()
+    _cabi.profile(False)
+    value = e * LAYERS / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss ---------------------------------
+    step_e2e()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    t0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    t1.record()
+    torch.cuda.synchronize()
+    e2e_ms = t0.elapsed_time(t1) / e2e_steps
+    e2e_value = e * LAYERS / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------
+    peaks = load_peaks()
+    roofline = dominant_kernel_roofline(kernels, args.steps, e, n, peaks)
+
+    # ---- CPU baseline: oracle port on a bounded sub-mesh ------------------------------------------------
+    cpu = cpu_baseline(steps=1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
+        "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, "
+                               "processor fwd+bwd", "nodes": n, "edges": e, "layers": LAYERS, "latent": LATENT,
+                   "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def dominant_kernel_roofline(kernels, steps, e, n, peaks):
+    """Algorithmic FLOPs per launch (recompute earns no credit) over the mean launch time."""
+    if not kernels:
+        return None
+    top = max(kernels, key=lambda k: k["ms"])
+    per_step_ms = top["ms"] / steps
+    rows_total = (e + n) * LAYERS          # every layer runs the tile kernels once over the edges and once over the nodes
+    flops_fwd = (e * F_EDGE + n * F_NODE_SUM) * LAYERS
+    algo = {"mlp_tile_tc_fwd": flops_fwd, "mlp_tile_tc_bwd": flops_fwd, "mlp_wgrad_tc": flops_fwd}.get(top["name"])
+    mean_ms = top["ms"] / top["launches"]
+    if algo is not None:
+        achieved = algo / (per_step_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        return {"kernel": top["name"], "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "mean_launch_ms": mean_ms, "launches_per_step": top["launches"] / steps,
+                "flops_per_step": algo, "rows_per_step": rows_total, "peak_source": peaks["source"] + ", sustained bf16"}
+    # an HBM-bound helper kernel dominates: report its bytes (reads + writes of 128-wide bf16 rows)
+    bytes_step = {"segment_reduce": (e + n) * 256 + e * 4, "segment_reduce_bwd": (e + n) * 256 + e * 4,
+                  "multi_segment_sum": (2 * e + n) * 256 + 2 * e * 4, "colsum": e * 256}.get(top["name"], 0) * LAYERS
+    achieved = bytes_step / (per_step_ms * 1e-3) / 1e9
+    return {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "mean_launch_ms": mean_ms, "peak_source": peaks["source"]}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's torch path on the host cores
+# ------------------------------------------------------------------------------------------------------
+CPU_SAMPLE_W, CPU_SAMPLE_H, CPU_SAMPLE_LAYERS = 1000, 125, 1
+
+
+def cpu_pass(state):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgn_oracle as orc
+    w, v0, e0, s, r, coef = state
+    for t in w.values():
+        t.grad = None
+    v = v0.clone().requires_grad_(True)
+    ed = e0.clone().requires_grad_(True)
+    out = orc.processor(w, "sum", "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
+    loss = (out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3
+    loss.backward()
+    return float(loss)
+
+
+def cpu_state():
+    from hgn_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = build_inputs(CPU_SAMPLE_W, CPU_SAMPLE_H, CPU_SAMPLE_LAYERS)
+    w = {k: t.clone().requires_grad_(True) for k, t in data["weights"].items()}
+    return (w, data["v0"], data["e0"], data["senders"], data["receivers"], data["coef_v"]), data["e"]
+
+
+def cpu_baseline(steps=1):
+    state, e = cpu_state()
+    cpu_pass(state)                      # untimed: first touch / thread pool start
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(state)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": e * CPU_SAMPLE_LAYERS / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "seconds_per_pass": dt,
+            "sample": f"{CPU_SAMPLE_W}x{CPU_SAMPLE_H} sub-mesh of the workload ({e} directed edges), {CPU_SAMPLE_LAYERS} layer, "
+                      "fwd+bwd, fp32, oracle/hgn_oracle.py (torch CPU ops = the reference's own arithmetic)"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    state, e = cpu_state()
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_pass(state)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(state)
+    dt = (time.perf_counter() - t0) / steps
+    value = e * CPU_SAMPLE_LAYERS / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = {CPU_SAMPLE_W}x{CPU_SAMPLE_H} sub-mesh of the cfg5 mesh ({e} directed edges), {CPU_SAMPLE_LAYERS} layer, fwd+bwd, "
+              "fp32, oracle port of the reference's torch/torch_scatter path on all host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (same seeded grid mesh family)",
+        "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, processor fwd+bwd",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace hgn {
@@ -14,6 +19,28 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+// ---- kernel timing registry ---------------------------------------------------------------------
+struct TimedLaunch { const char* name; cudaEvent_t start, stop; };
+static bool g_profile_on = false;
+static std::vector<TimedLaunch> g_launches;
+static std::mutex g_profile_mutex;
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t st) : name_(name), st_(st), start_(nullptr), on_(g_profile_on) {
+  if (on_) {
+    cudaEventCreate(&start_);
+    cudaEventRecord(start_, st_);
+  }
+}
+KernelTimer::~KernelTimer() {
+  if (on_) {
+    cudaEvent_t stop;
+    cudaEventCreate(&stop);
+    cudaEventRecord(stop, st_);
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    g_launches.push_back({name_, start_, stop});
+  }
 }
 
 // fp32 path (mlp_f32.cu)
@@ -112,6 +139,45 @@ extern "C" int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunk
                            grad_gamma, grad_beta, workspace, workspace_bytes, st);
   set_error("mlp_backward: unknown dtype %d", dtype);
   return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_profile_enable(int on) { g_profile_on = on != 0; return HGN_OK; }
+
+extern "C" int hgn_profile_reset(void) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  for (auto& l : g_launches) { cudaEventDestroy(l.start); cudaEventDestroy(l.stop); }
+  g_launches.clear();
+  return HGN_OK;
+}
+
+extern "C" size_t hgn_profile_report(char* buf, size_t buf_bytes) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long, double>> agg;
+  std::vector<std::string> order;
+  {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    for (auto& l : g_launches) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, l.start, l.stop) != cudaSuccess) { cudaGetLastError(); continue; }
+      auto it = agg.find(l.name);
+      if (it == agg.end()) { order.push_back(l.name); agg[l.name] = {1, ms}; }
+      else { it->second.first += 1; it->second.second += ms; }
+    }
+  }
+  std::string out = "[";
+  for (size_t i = 0; i < order.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"launches\": %ld, \"ms\": %.6f}", i ? ", " : "", order[i].c_str(),
+             agg[order[i]].first, agg[order[i]].second);
+    out += line;
+  }
+  out += "]";
+  if (buf && buf_bytes) {
+    const size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
 }
 
 extern "C" int hgn_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream) {

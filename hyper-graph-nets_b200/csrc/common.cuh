@@ -38,6 +38,17 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+// RAII CUDA-event bracket around one kernel launch (active only after hgn_profile_enable(1))
+struct KernelTimer {
+  KernelTimer(const char* name, cudaStream_t st);
+  ~KernelTimer();
+  const char* name_;
+  cudaStream_t st_;
+  cudaEvent_t start_;
+  bool on_;
+};
+#define HGN_TIMED(name, st) ::hgn::KernelTimer _hgn_timer_##__LINE__(name, st)
+
 constexpr int kD = 128;   // latent width the MLP tile kernels are specialised for (flag.py:57)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -493,6 +493,7 @@ __global__ void reduce_w0_kernel(const float* __restrict__ partial, int parts, i
 void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks, float* gW0, float* gW1, float* gW2, cudaStream_t st) {
   const int n_z = n_chunks + 2;
   const int64_t k0 = int64_t(n_chunks) * kD, blk = int64_t(kD) * kD;
+  HGN_TIMED("reduce_weight_partials", st);
   reduce_w0_kernel<<<unsigned(ceil_div(kD * k0, 256)), 256, 0, st>>>(partial, parts, n_z, n_chunks, gW0);
   reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks) * blk, parts, int64_t(n_z) * blk, blk, gW1);
   reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks + 1) * blk, parts, int64_t(n_z) * blk, blk, gW2);
@@ -540,6 +541,7 @@ int mlp_f32_forward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
     HGN_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured = true;
   }
+  HGN_TIMED("mlp_fwd_f32", st);
   mlp_fwd_f32_kernel<<<unsigned(ceil_div(rows, kTileRows)), kThreads, smem, st>>>(rows, *ch, static_cast<const float*>(packed),
                                                                                static_cast<const float*>(resid), resid_off,
                                                                                static_cast<float*>(out));
@@ -572,6 +574,7 @@ int mlp_f32_backward(int64_t rows, const hgn_chunks* ch, const void* packed, con
   for (int64_t slab0 = 0; slab0 < rows || pass == 0; slab0 += L.slab_rows, ++pass) {
     const int64_t this_rows = rows - slab0 < L.slab_rows ? rows - slab0 : L.slab_rows;
     if (this_rows > 0) {
+      HGN_TIMED("mlp_bwd_f32", st);
       mlp_bwd_f32_kernel<<<unsigned(ceil_div(this_rows, kTileRows)), kThreads, smem_bwd, st>>>(
           rows, slab0, L.slab_rows, *ch, static_cast<const float*>(packed), static_cast<const float*>(grad_out), go, G2, G1, G0, H1,
           H2, ln_partial, pass > 0, resid_chunk);
@@ -584,8 +587,10 @@ int mlp_f32_backward(int64_t rows, const hgn_chunks* ch, const void* packed, con
         HGN_CUDA_OK(cudaMemsetAsync(ln_partial + launched * 256, 0, size_t(L.tiles - launched) * 256 * 4, st));
     }
     dim3 grid(unsigned(L.parts), unsigned(n_z));
+    { HGN_TIMED("mlp_wgrad_f32", st);
     mlp_wgrad_f32_kernel<<<grid, kThreads, smem_wg, st>>>(rows, slab0, L.slab_rows, L.rows_per_part, *ch, G0, G1, G2, H1, H2, partial,
                                                           bias_partial, pass > 0);
+    }
     HGN_LAUNCH_OK("mlp_wgrad_f32");
     if (rows == 0) break;
   }

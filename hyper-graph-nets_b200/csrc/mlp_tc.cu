@@ -643,6 +643,7 @@ size_t mlp_tc_packed_bytes(int n_chunks) { return PackedTc(n_chunks).total; }
 int mlp_tc_pack(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
                 const float* b2, const float* gamma, const float* beta, void* packed, cudaStream_t st) {
   const int64_t n = int64_t(n_chunks) * kD * kD;
+  HGN_TIMED("pack_tc", st);
   pack_tc_kernel<<<unsigned(ceil_div(n, 256)), 256, 0, st>>>(n_chunks, W0, b0, W1, b1, W2, b2, gamma, beta, static_cast<uint8_t*>(packed));
   HGN_LAUNCH_OK("pack_tc");
   return HGN_OK;
@@ -679,6 +680,7 @@ int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const
   const int64_t tiles = ceil_div(rows, kTile);
   const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
   BwdArgs none{};
+  HGN_TIMED("mlp_tile_tc_fwd", st);
   mlp_tile_tc_kernel<false><<<grid, kTileThreads, S.total, st>>>(rows, tiles, 0, *ch, static_cast<const uint8_t*>(packed), resident ? 1 : 0,
                                                                  static_cast<const __nv_bfloat16*>(resid), resid_off,
                                                                  static_cast<__nv_bfloat16*>(out), none);
@@ -748,13 +750,16 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
     if (this_rows > 0) {
       const int64_t tiles = ceil_div(this_rows, kTile);
       const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
+      HGN_TIMED("mlp_tile_tc_bwd", st);
       mlp_tile_tc_kernel<true><<<grid, kTileThreads, S.total, st>>>(rows, tiles, slab0, *ch, static_cast<const uint8_t*>(packed),
                                                                     resident ? 1 : 0, nullptr, 0, nullptr, bw);
       HGN_LAUNCH_OK("mlp_bwd_tc");
     }
     wa.accumulate = pass > 0;
     dim3 grid(unsigned(L.parts), unsigned(L.groups));
+    { HGN_TIMED("mlp_wgrad_tc", st);
     mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(rows, slab0, L.slab_rows, L.rows_per_part, *ch, wa);
+    }
     HGN_LAUNCH_OK("mlp_wgrad_tc");
     // bias / LayerNorm vector gradients: column sums of G2, G1, G0, P and grad_out over this slab
     const void* mats[5] = {bw.G2, bw.G1, bw.G0, bw.P, bw.grad_out ? (const void*)(bw.grad_out + slab0 * kD) : nullptr};

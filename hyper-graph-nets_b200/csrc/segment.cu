@@ -235,6 +235,7 @@ static int segment_reduce_impl(const T* data, int64_t E, int32_t D, const int32_
   if (S == 0) return HGN_OK;
   if (D % 4 == 0) {
     const int64_t blocks = ceil_div(S * 32, 256);
+    HGN_TIMED("segment_reduce", st);
     segment_reduce_vec_kernel<T><<<unsigned(blocks), 256, 0, st>>>(data, D, perm, rowptr, S, out_sum, out_mean, out_max,
                                                                 out_min, argmax, argmin, accumulate_sum);
   } else {
@@ -252,6 +253,7 @@ static int segment_reduce_bwd_impl(int64_t E, int32_t D, const int32_t* ids, con
                                    const int32_t* argmin, T* grad, int accumulate, cudaStream_t st) {
   if (E == 0) return HGN_OK;
   if (D % 4 == 0) {
+    HGN_TIMED("segment_reduce_bwd", st);
     segment_reduce_bwd_vec_kernel<T><<<unsigned(ceil_div(E * 32, 256)), 256, 0, st>>>(E, D, ids, rowptr, g_sum, g_mean, g_max,
                                                                                    g_min, argmax, argmin, grad, accumulate);
   } else {
@@ -410,6 +412,7 @@ extern "C" int hgn_colsum(int dtype, const void* x, int64_t rows, int32_t D, flo
   const int64_t blocks = hgn::ceil_div(rows, hgn::kColsumRowsPerBlock);
   if (workspace_bytes < size_t(blocks) * D * 4 || !workspace) { hgn::set_error("colsum: workspace too small"); return HGN_ERR_WORKSPACE; }
   float* partial = static_cast<float*>(workspace);
+  HGN_TIMED("colsum", st);
   if (dtype == HGN_F32) hgn::colsum_partial_kernel<float><<<unsigned(blocks), 256, 0, st>>>((const float*)x, rows, D, partial);
   else if (dtype == HGN_BF16) hgn::colsum_partial_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, st>>>((const __nv_bfloat16*)x, rows, D, partial);
   else { hgn::set_error("colsum: unknown dtype %d", dtype); return HGN_ERR_INVALID_ARGUMENT; }
@@ -459,6 +462,7 @@ extern "C" int hgn_multi_segment_sum(int dtype, const hgn_segment_sources* sourc
   if (S == 0) return HGN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned blocks = unsigned(hgn::ceil_div(S * 32, 256));
+  HGN_TIMED("multi_segment_sum", st);
   if (dtype == HGN_F32) hgn::multi_segment_sum_kernel<float><<<blocks, 256, 0, st>>>(*sources, S, D, (const float*)base, (float*)out);
   else if (dtype == HGN_BF16) hgn::multi_segment_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*sources, S, D, (const __nv_bfloat16*)base, (__nv_bfloat16*)out);
   else { hgn::set_error("multi_segment_sum: unknown dtype %d", dtype); return HGN_ERR_INVALID_ARGUMENT; }

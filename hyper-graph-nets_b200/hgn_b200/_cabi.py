@@ -50,6 +50,9 @@ SIGNATURES = {
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hgn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "hgn_profile_enable": (c_int, [c_int]),
+    "hgn_profile_reset": (c_int, []),
+    "hgn_profile_report": (c_size_t, [c_char_p, c_size_t]),
     "hgn_copy_h2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "hgn_copy_d2h": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }
@@ -113,3 +116,21 @@ def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise HgnError("hgn_b200 kernels take CUDA tensors")
+
+
+def profile(enable: bool) -> None:
+    """Switch the library's per-kernel CUDA-event timing on/off (clears earlier records when enabling)."""
+    lib = load()
+    if enable:
+        lib.hgn_profile_reset()
+    lib.hgn_profile_enable(1 if enable else 0)
+
+
+def profile_report():
+    """[{'name', 'launches', 'ms'}] since the last ``profile(True)`` (synchronises the device)."""
+    import json
+    lib = load()
+    n = lib.hgn_profile_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.hgn_profile_report(buf, n + 16)
+    return json.loads(buf.value.decode())

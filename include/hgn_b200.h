@@ -157,6 +157,16 @@ int hgn_rows_gather(int dtype, const void* src, const int32_t* idx, int64_t n, i
 int hgn_rows_scatter(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst,
                      int accumulate, void* stream);
 
+/* ---- kernel timing (tracing hook; the reference only has wall-clock time.time() around a batch,
+ * src/algorithms/MeshSimulator.py:135-155) ----------------------------------------------------------
+ * When enabled, every kernel launch inside the library is bracketed by CUDA events on the launching
+ * stream.  hgn_profile_report synchronises the device and writes a JSON array
+ * [{"name": "...", "launches": n, "ms": total_ms}, ...] into buf (truncated to buf_bytes, always
+ * NUL-terminated) and returns the number of bytes needed. */
+int hgn_profile_enable(int on);
+int hgn_profile_reset(void);
+size_t hgn_profile_report(char* buf, size_t buf_bytes);
+
 /* ---- host-buffer convenience (the end-to-end path timed by bench.py "e2e") ---------------------
  * Not part of the reference API; copies pinned host rows to the device and back on `stream`. */
 int hgn_copy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
