@@ -14,11 +14,30 @@ namespace hgn {
 
 static thread_local char g_error[512] = "";
 
+static uint32_t* g_debug_host = nullptr;
+static uint32_t* g_debug_dev = nullptr;
+
+uint32_t* debug_buffer_device() {
+  if (g_debug_dev == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_debug_host), 256, cudaHostAllocMapped) == cudaSuccess) {
+      memset(g_debug_host, 0, 256);
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_debug_dev), g_debug_host, 0) != cudaSuccess) g_debug_dev = nullptr;
+    }
+    cudaGetLastError();
+  }
+  return g_debug_dev;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
-  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  int n = vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+  if (g_debug_host != nullptr && g_debug_host[0] == 0xB200DEADu && n > 0 && n < int(sizeof(g_error)) - 160) {
+    const uint32_t* w = g_debug_host;
+    snprintf(g_error + n, sizeof(g_error) - n, " [device stall record: tag=%u block=%u thread=%u words=%08x %08x %08x %08x %08x %08x]", w[1], w[2],
+             w[3], w[4], w[5], w[6], w[7], w[8], w[9]);
+  }
 }
 
 // ---- kernel timing registry ---------------------------------------------------------------------

@@ -70,9 +70,9 @@ __global__ void pack_tc_kernel(int n_chunks, const float* W0, const float* b0, c
 // ---- shared-memory map of the tile kernel ------------------------------------------------------------
 struct TileSmem {
   int w0_panels;          // 2*n_chunks when resident else 0
-  uint32_t w0, w1, w2, stages, params, bars, total;
+  uint32_t w0, w1, w2, stages, w0b, params, bars, total;
   int stage_bytes;
-  __host__ __device__ TileSmem(int n_chunks, bool resident) {
+  __host__ __device__ TileSmem(int n_chunks, bool resident, bool bwd) {
     w0_panels = resident ? 2 * n_chunks : 0;
     stage_bytes = resident ? kChunkBytes : 2 * kChunkBytes;
     uint32_t o = 0;
@@ -80,12 +80,21 @@ struct TileSmem {
     w1 = o; o += 2 * kPanel;
     w2 = o; o += 2 * kPanel;
     stages = o; o += uint32_t(kStages) * stage_bytes;
+    w0b = o; o += (!resident && bwd) ? kChunkBytes : 0;     // streamed W0: panel pair for the dX GEMMs
     params = o; o += 5 * kD * 4;
     bars = o; o += 128;
     total = o;
   }
 };
-enum { kBarFull = 0, kBarEmpty = 2, kBarAccFull = 4, kBarEpiDone = 6, kBarTmemPtr = 8 };
+// mbarrier slots (uint64 each) inside the 128-byte barrier block
+// (16 slots).  kBarAcc + (tile % 6): tile i uses accumulator i%3 and epilogue group i%2, so each of the six
+// barriers has ONE waiting group that consumes its phases in program order.  kBarEpi: "step drained, next A
+// operand written"; kBarDone: "tile finished, accumulator free" -- split because a group can publish the first
+// step of its next tile before the MMA warp has looked at the previous tile's last signal; on one barrier that
+// would put it two phases ahead and the parity test could no longer tell them apart.
+enum { kBarFull = 0, kBarEmpty = 2, kBarAcc = 4, kBarEpi = 10, kBarDone = 12, kBarTmemPtr = 14, kBarW0b = 15 };
+constexpr int kAccSlots = 3;                    // TMEM accumulators [0,128) [128,256) [256,384)
+constexpr uint32_t kAopCol = 384;               // bf16 A operands of the two epilogue groups: [384,448) [448,512)
 
 // copy a [128][128] bf16 row-major block (row pitch `ld` elements) into two SW128 panels
 __device__ __forceinline__ void load_weight_block(uint32_t smem_dst, const __nv_bfloat16* __restrict__ g, int64_t ld, int tid, int nthreads) {
@@ -116,7 +125,10 @@ __device__ __forceinline__ void issue_ts_gemm(uint32_t acc, uint32_t a_tmem, uin
 }
 
 // ---- tile kernel ---------------------------------------------------------------------------------------
-// Steps per tile: forward 0:L0 1:L1 2:L2 ; backward adds 3:dH2=dY W2  4:dH1=dH2' W1  5+c: dX_c = dH1' W0[:,c]
+// Steps per tile: forward 0:L0 1:L1 2:L2 ; backward adds 3:dH2=dY W2  4:dH1=dH2' W1  5+c: dX_c = dH1' W0[:,c].
+// Scheduling: tile i of a CTA uses accumulator i%3 and epilogue group i%2.  The MMA warp is event driven: it
+// streams layer 0 of the next tile chunk by chunk as the ring fills, and issues step k+1 of a tile the moment
+// its epilogue group reports step k drained -- so gather latency, tensor work and epilogue work overlap.
 template <bool kBwd>
 __global__ void __launch_bounds__(kTileThreads, 1)
 mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch, const uint8_t* __restrict__ packed,
@@ -124,7 +136,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
                    BwdArgs bw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nch = ch.n_chunks;
-  const TileSmem S(nch, w0_resident != 0);
+  const TileSmem S(nch, w0_resident != 0, kBwd);
   const PackedTc P(nch);
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SW128 atoms need 1024-byte alignment
@@ -146,7 +158,9 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
     for (int i = tid; i < 5 * kD; i += kTileThreads) sparams[i] = pg[i];
     if (tid == 0) {
       for (int s = 0; s < kStages; ++s) { mbar_init(&bars[kBarFull + s], kProdThreads / kStages); mbar_init(&bars[kBarEmpty + s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&bars[kBarAccFull + s], 1); mbar_init(&bars[kBarEpiDone + s], kEpiThreads / 2); }
+      for (int s = 0; s < 6; ++s) mbar_init(&bars[kBarAcc + s], 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars[kBarEpi + s], kEpiThreads / 2); mbar_init(&bars[kBarDone + s], kEpiThreads / 2); }
+      mbar_init(&bars[kBarW0b], 1);
       mbar_init_fence();
     }
     if (warp == 12) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[kBarTmemPtr]));
@@ -158,143 +172,194 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
   }
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars[kBarTmemPtr]);
   const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles b, b+G, ...
-  const bool stream_w0_bwd = kBwd && !w0_resident;   // dX GEMMs need the W0 panels again
 
   if (warp >= 8 && warp < 12) {
     // =============================== producers ====================================================
+    // ring slot g holds chunk (g % nch) of this CTA's tile (g / nch); group `g & 1` fills it.
     const int ptid = tid - kEpiThreads;          // 0..127
-    const int group = ptid >> 6;                 // 0/1: owns stage `group`
+    const int group = ptid >> 6;
     const int gt = ptid & 63;
     if (gt == 0) mbar_arrive(&bars[kBarEmpty + group]);   // the ring starts empty
     const uint32_t stage_addr = sbase + S.stages + group * S.stage_bytes;
     const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
-    int64_t g = 0;                               // running ring-slot counter of this CTA
-    // one ring slot: chunk c of tile `row0` (A operand, when with_a) plus its W0 panel pair (when streamed)
-    auto produce = [&](int64_t row0, int c, bool with_a) {
-      if ((g & 1) == group) {
-        mbar_wait(&bars[kBarEmpty + group], uint32_t(g >> 1) & 1);
-        if (with_a) {
-          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(ch.src[c]);
-          const int32_t* idx = ch.idx[c];
-          const int64_t roff = ch.row_offset[c];
-#pragma unroll 4
-          for (int j = 0; j < 32; ++j) {
-            const int q = gt + 64 * j;             // 2048 16-byte pieces: row = q/16, piece = q%16
-            const int row = q >> 4, c16 = q & 15;
-            const int64_t grow = row0 + row;
-            const bool valid = grow < rows;
-            int64_t srow = 0;
-            if (valid) srow = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
-            cp_async16_zfill(stage_addr + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), src + srow * kD + c16 * 8, valid);
-          }
-        }
-        if (!w0_resident) load_weight_block(stage_addr + kChunkBytes, w0g + c * kD, k0, gt, 64);
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_async_smem();
-        mbar_arrive(&bars[kBarFull + group]);
+    const int64_t n_slots = my_tiles * nch;
+    const int c16 = gt & 15, rbase = gt >> 4;    // this thread copies 16-byte piece c16 of rows rbase + 4 j
+    // all 32 source-row indices of a slot are fetched in one batch, one slot ahead of the copies
+    auto fetch_rows = [&](int64_t g, int32_t (&srow)[32]) {
+      const int c = int(g % nch);
+      const int64_t row0 = slab0 + (blockIdx.x + (g / nch) * gridDim.x) * kTile;
+      const int32_t* idx = ch.idx[c];
+      const int64_t roff = ch.row_offset[c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t grow = row0 + rbase + 4 * j;
+        srow[j] = -1;
+        if (grow < rows) srow[j] = idx ? __ldg(idx + grow) : int32_t(grow + roff);
       }
-      ++g;
     };
-    for (int64_t it0 = 0; it0 < my_tiles; it0 += 2) {
-      const int n_in_pair = (it0 + 1 < my_tiles) ? 2 : 1;
-      // layer-0 operands in the MMA issuer's order: tile slot 0 chunk by chunk, then slot 1
-      for (int slot = 0; slot < n_in_pair; ++slot)
-        for (int c = 0; c < nch; ++c) produce(slab0 + (blockIdx.x + (it0 + slot) * gridDim.x) * kTile, c, true);
-      // backward with a streamed W0: the dX GEMMs run chunk-major over the pair
-      if (stream_w0_bwd)
-        for (int c = 0; c < nch; ++c)
-          for (int slot = 0; slot < n_in_pair; ++slot) produce(0, c, false);
+    int32_t cur[32], nxt[32];
+    int64_t g = group;
+    if (g < n_slots) fetch_rows(g, cur);
+    for (; g < n_slots; g += 2) {
+      const int c = int(g % nch);
+      mbar_wait(&bars[kBarEmpty + group], uint32_t(g >> 1) & 1, 1);
+      const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(ch.src[c]);
+      const uint32_t dst0 = stage_addr + (c16 >> 3) * kPanel;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool valid = cur[j] >= 0;
+        cp_async16_zfill(dst0 + sw128_chunk(rbase + 4 * j, c16 & 7), src + int64_t(valid ? cur[j] : 0) * kD + c16 * 8, valid);
+      }
+      if (!w0_resident) load_weight_block(stage_addr + kChunkBytes, w0g + c * kD, k0, gt, 64);
+      cp_async_commit();
+      if (g + 2 < n_slots) fetch_rows(g + 2, nxt);     // index loads overlap the row copies in flight
+      cp_async_wait<0>();
+      fence_async_smem();
+      mbar_arrive(&bars[kBarFull + group]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) cur[j] = nxt[j];
     }
   } else if (warp == 12) {
-    // =============================== MMA issuer ===================================================
-    if (lane == 0) {
-      const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);
-      int64_t g = 0;
-      uint32_t epi_waits[2] = {0, 0};
-      for (int64_t it0 = 0; it0 < my_tiles; it0 += 2) {
-        const int n_in_pair = (it0 + 1 < my_tiles) ? 2 : 1;
-        for (int step = 0; step < n_steps; ++step) {
-          for (int slot = 0; slot < n_in_pair; ++slot) {
-            const uint32_t acc = tmem_base + slot * 256;
-            const uint32_t aop = acc + 128;
-            // step 0: previous tile's accumulator drained; later steps: A operand written by the epilogue
-            mbar_wait(&bars[kBarEpiDone + slot], epi_waits[slot] & 1);
-            ++epi_waits[slot];
-            fence_after_sync();
-            if (step == 0) {
-              for (int c = 0; c < nch; ++c, ++g) {
-                const int stage = int(g & 1);
-                mbar_wait(&bars[kBarFull + stage], uint32_t(g >> 1) & 1);
-                fence_after_sync();
-                const uint32_t a_addr = sbase + S.stages + stage * S.stage_bytes;
-                const uint32_t b_addr = w0_resident ? sbase + S.w0 + c * kChunkBytes : a_addr + kChunkBytes;
+    // =============================== MMA warp (lane 0 issues) =====================================
+    const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);
+    int64_t t_l0 = 0, g = 0, done = 0;
+    int c_l0 = 0;
+    int64_t wg_tile[2] = {0, 1};
+    int wg_step[2] = {0, 0};
+    uint32_t wg_sig[2] = {0, 0}, wg_fin[2] = {0, 0};
+    uint32_t acc_busy = 0, w0b_uses = 0, idle = 0;
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    while (done < my_tiles) {
+      bool progressed = false;
+      // lane 0 polls the barriers once per round and broadcasts, so the whole warp takes the same path
+      uint32_t ev = 0;
+      if (lane == 0) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                  const uint32_t koff = (ks >> 2) * kPanel + (ks & 3) * 32;
-                  mma_ss(acc, sdesc_kmajor(a_addr + koff), sdesc_kmajor(b_addr + koff), idesc_kk, (c | ks) != 0);
-                }
-                mma_commit(&bars[kBarEmpty + stage]);
-              }
-            } else if (step == 1) {
-              issue_ts_gemm(acc, aop, sbase + S.w1, 0);
-            } else if (step == 2) {
-              issue_ts_gemm(acc, aop, sbase + S.w2, 0);
-            } else if (step == 3) {
-              issue_ts_gemm(acc, aop, sbase + S.w2, 1);
-            } else if (step == 4) {
-              issue_ts_gemm(acc, aop, sbase + S.w1, 1);
-            } else {
+        for (int w = 0; w < 2; ++w)
+          if (wg_tile[w] < t_l0 &&
+              (wg_step[w] == n_steps - 1 ? mbar_test(&bars[kBarDone + w], wg_fin[w] & 1) : mbar_test(&bars[kBarEpi + w], wg_sig[w] & 1)))
+            ev |= 1u << w;
+        if (t_l0 < my_tiles && (c_l0 > 0 || !((acc_busy >> int(t_l0 % kAccSlots)) & 1u)) &&
+            mbar_test(&bars[kBarFull + int(g & 1)], uint32_t(g >> 1) & 1)) ev |= 4u;
+      }
+      ev = __shfl_sync(0xffffffffu, ev, 0);
+      // ---- steps 1.. of the tiles whose epilogue group has reported the previous step drained -----
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int64_t t = wg_tile[w];
+        if ((ev >> w) & 1u) {
+          fence_after_sync();
+          const int k = wg_step[w]++;
+          const int slot = int(t % kAccSlots);
+          if (k == n_steps - 1) {                      // tile finished: its accumulator is free again
+            ++wg_fin[w];
+            acc_busy &= ~(1u << slot);
+            wg_tile[w] += 2;
+            wg_step[w] = 0;
+            ++done;
+          } else {
+            ++wg_sig[w];
+            const int step = k + 1;
+            const uint32_t acc = tmem_base + slot * 128;
+            const uint32_t aop = tmem_base + kAopCol + w * 64;
+            if (step >= 5 && !w0_resident) {
+              // streamed W0: fetch the panel pair of chunk c for this dX GEMM (the warp blocks ~1 us; only
+              // node MLPs with more than 3 input chunks take this path)
               const int c = step - 5;
-              if (w0_resident) {
-                issue_ts_gemm(acc, aop, sbase + S.w0 + c * kChunkBytes, 1);
-              } else {
-                // W0 panels stream through the ring again, chunk-major over the pair like the producers walk it
-                const int64_t gg = g + int64_t(c) * n_in_pair + slot;
-                const int stage = int(gg & 1);
-                mbar_wait(&bars[kBarFull + stage], uint32_t(gg >> 1) & 1);
-                fence_after_sync();
-                issue_ts_gemm(acc, aop, sbase + S.stages + stage * S.stage_bytes + kChunkBytes, 1);
-                mma_commit(&bars[kBarEmpty + stage]);
-              }
+              if (w0b_uses > 0) mbar_wait(&bars[kBarW0b], (w0b_uses - 1) & 1);
+              load_weight_block(sbase + S.w0b, w0g + c * kD, k0, lane, 32);
+              cp_async_commit();
+              cp_async_wait<0>();
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) { issue_ts_gemm(acc, aop, sbase + S.w0b, 1); mma_commit(&bars[kBarW0b]); }
+              ++w0b_uses;
+            } else if (lane == 0) {
+              if (step == 1) issue_ts_gemm(acc, aop, sbase + S.w1, 0);
+              else if (step == 2) issue_ts_gemm(acc, aop, sbase + S.w2, 0);
+              else if (step == 3) issue_ts_gemm(acc, aop, sbase + S.w2, 1);
+              else if (step == 4) issue_ts_gemm(acc, aop, sbase + S.w1, 1);
+              else issue_ts_gemm(acc, aop, sbase + S.w0 + (step - 5) * kChunkBytes, 1);
             }
-            mma_commit(&bars[kBarAccFull + slot]);
+            if (lane == 0) mma_commit(&bars[kBarAcc + int(t % 6)]);
+            __syncwarp();
+          }
+          progressed = true;
+        }
+      }
+      // ---- layer 0 of the next tile: one chunk per visit, as soon as its ring slot is full --------
+      if (ev & 4u) {
+        const int slot = int(t_l0 % kAccSlots);
+        {
+          const int stage = int(g & 1);
+          {
+            fence_after_sync();
+            if (lane == 0) {
+              const uint32_t acc = tmem_base + slot * 128;
+              const uint32_t a_addr = sbase + S.stages + stage * S.stage_bytes;
+              const uint32_t b_addr = w0_resident ? sbase + S.w0 + c_l0 * kChunkBytes : a_addr + kChunkBytes;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t koff = (ks >> 2) * kPanel + (ks & 3) * 32;
+                mma_ss(acc, sdesc_kmajor(a_addr + koff), sdesc_kmajor(b_addr + koff), idesc_kk, (c_l0 | ks) != 0);
+              }
+              mma_commit(&bars[kBarEmpty + stage]);
+              if (c_l0 + 1 == nch) mma_commit(&bars[kBarAcc + int(t_l0 % 6)]);
+            }
+            __syncwarp();
+            acc_busy |= 1u << slot;
+            ++g;
+            if (++c_l0 == nch) { c_l0 = 0; ++t_l0; }
+            progressed = true;
           }
         }
-        if (stream_w0_bwd) g += int64_t(n_in_pair) * nch;
+      }
+      if (!progressed) {
+        __nanosleep(20);
+        if (++idle > (1u << 22)) {
+          if (lane == 0)
+            debug_record(900u + uint32_t(kBwd), uint32_t(t_l0) | (uint32_t(c_l0) << 16), uint32_t(g), uint32_t(done) | (uint32_t(my_tiles) << 16),
+                         uint32_t(wg_tile[0]) | (uint32_t(wg_tile[1]) << 16), uint32_t(wg_step[0]) | (uint32_t(wg_step[1]) << 8) | (acc_busy << 16),
+                         wg_sig[0] | (wg_sig[1] << 16));
+          __trap();
+        }
+      } else {
+        idle = 0;
       }
     }
   } else {
     // =============================== epilogue groups ==============================================
-    const int slot = warp >> 2;                       // warps 0-3 -> slot 0, warps 4-7 -> slot 1
+    const int wg = warp >> 2;                         // warps 0-3 -> group 0 (even tiles), 4-7 -> group 1 (odd tiles)
     const int r = (warp & 3) * 32 + lane;             // tile row = TMEM lane
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t acc = tmem_base + slot * 256 + lane_addr;
-    const uint32_t aop = acc + 128;
-    mbar_arrive(&bars[kBarEpiDone + slot]);           // accumulator slot starts free
-    uint32_t acc_waits = 0;
-    auto wait_acc = [&]() {
-      mbar_wait(&bars[kBarAccFull + slot], acc_waits & 1);
-      ++acc_waits;
-      fence_after_sync();
-    };
-    auto signal_done = [&]() {
-      fence_before_sync();
-      mbar_arrive(&bars[kBarEpiDone + slot]);
-    };
+    const uint32_t aop = tmem_base + kAopCol + wg * 64 + lane_addr;
     const float* b2 = sparams + 2 * kD;
     const float* gam = sparams + 3 * kD;
     const float* bet = sparams + 4 * kD;
-    for (int64_t it = slot; it < my_tiles; it += 2) {
+    for (int64_t it = wg; it < my_tiles; it += 2) {
+      const int slot = int(it % kAccSlots);
+      const uint32_t acc = tmem_base + slot * 128 + lane_addr;
+      uint32_t acc_phase = uint32_t((it / 6) * n_steps);   // completions of this (group, accumulator) barrier so far
+      uint32_t steps_done = 0;
+      auto wait_acc = [&]() {
+        mbar_wait(&bars[kBarAcc + int(it % 6)], acc_phase & 1, 100 + int(steps_done));
+        ++acc_phase;
+        fence_after_sync();
+      };
+      auto signal_done = [&]() {
+        fence_before_sync();
+        mbar_arrive(&bars[(++steps_done == uint32_t(n_steps) ? kBarDone : kBarEpi) + wg]);
+      };
       const int64_t grow = slab0 + (blockIdx.x + it * gridDim.x) * kTile + r;
       const bool valid = grow < rows;
       const int64_t lrow = valid ? grow - slab0 : 0;   // row inside the slab workspaces
       uint32_t mask1[4] = {0, 0, 0, 0}, mask2[4] = {0, 0, 0, 0};   // ReLU masks (backward)
       // ---- hidden layers: bias + ReLU -> bf16 A operand in TMEM -------------------------------
+#pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
         wait_acc();
         const float* bias = sparams + layer * kD;
-        uint4* hws = kBwd ? reinterpret_cast<uint4*>((layer == 0 ? bw.H1 : bw.H2) + lrow * kD) : nullptr;
+        __nv_bfloat16* hws = kBwd ? (layer == 0 ? bw.H1 : bw.H2) + lrow * kD : nullptr;
 #pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32];
@@ -313,10 +378,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           tmem_st8(aop + cg * 16 + 8, h + 8);
           if (kBwd) {
             if (layer == 0) mask1[cg] = m; else mask2[cg] = m;
-            if (valid) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) hws[cg * 4 + q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-            }
+            if (valid) { stg256(hws + cg * 32, h); stg256(hws + cg * 32 + 16, h + 8); }
           }
         }
         tmem_st_wait();
@@ -345,79 +407,68 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
       }
       const float rstd = rsqrtf(sq * (1.0f / kD) + kEps);
       if (!kBwd) {
-        // ---- forward: affine, residual, store -------------------------------------------------
-        const uint4* rp = reinterpret_cast<const uint4*>(resid + (valid ? grow + resid_off : 0) * kD);
-        uint4* op = reinterpret_cast<uint4*>(out + (valid ? grow : 0) * kD);
+        // ---- forward: affine, residual, store (32-byte sectors per lane) ----------------------
+        const __nv_bfloat16* rp = resid + (valid ? grow + resid_off : 0) * kD;
+        __nv_bfloat16* op = out + (valid ? grow : 0) * kD;
 #pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
           if (valid) {
+            uint32_t rw[16], ow[16];
+            ldg256(rp + cg * 32, rw);
+            ldg256(rp + cg * 32 + 16, rw + 8);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rv = __ldg(rp + cg * 4 + q);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-              uint32_t ow[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int col = cg * 32 + q * 8 + t * 2;
-                const float y0 = (__uint_as_float(v[q * 8 + t * 2]) + b2[col] - mean) * rstd * gam[col] + bet[col];
-                const float y1 = (__uint_as_float(v[q * 8 + t * 2 + 1]) + b2[col + 1] - mean) * rstd * gam[col + 1] + bet[col + 1];
-                ow[t] = pack_bf16(bf16_lo(rw[t]) + y0, bf16_hi(rw[t]) + y1);
-              }
-              op[cg * 4 + q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            for (int j = 0; j < 16; ++j) {
+              const int col = cg * 32 + 2 * j;
+              const float y0 = (__uint_as_float(v[2 * j]) + b2[col] - mean) * rstd * gam[col] + bet[col];
+              const float y1 = (__uint_as_float(v[2 * j + 1]) + b2[col + 1] - mean) * rstd * gam[col + 1] + bet[col + 1];
+              ow[j] = pack_bf16(bf16_lo(rw[j]) + y0, bf16_hi(rw[j]) + y1);
             }
+            stg256(op + cg * 32, ow);
+            stg256(op + cg * 32 + 16, ow + 8);
           }
         }
         signal_done();
       } else {
         // ---- backward: LayerNorm backward -> dY (A operand) ; P = dO * yhat for the gamma gradient --
-        const uint4* gop = reinterpret_cast<const uint4*>(bw.grad_out + (valid ? grow : 0) * kD);
-        uint4* pws = reinterpret_cast<uint4*>(bw.P + lrow * kD);
+        const __nv_bfloat16* gop = bw.grad_out + (valid ? grow : 0) * kD;
+        __nv_bfloat16* pws = bw.P + lrow * kD;
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          uint32_t dpk[16];
+          uint32_t gw[16], pw[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 gv = make_uint4(0, 0, 0, 0);
-            if (valid) gv = __ldg(gop + cg * 4 + q);
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-            uint32_t pw[4];
+          for (int j = 0; j < 16; ++j) gw[j] = 0u;
+          if (valid) { ldg256(gop + cg * 32, gw); ldg256(gop + cg * 32 + 16, gw + 8); }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int col = cg * 32 + q * 8 + t * 2;
-              const float yh0 = (__uint_as_float(v[q * 8 + t * 2]) + b2[col] - mean) * rstd;
-              const float yh1 = (__uint_as_float(v[q * 8 + t * 2 + 1]) + b2[col + 1] - mean) * rstd;
-              const float d0 = bf16_lo(gw[t]), d1 = bf16_hi(gw[t]);
-              const float dy0 = d0 * gam[col], dy1 = d1 * gam[col + 1];
-              m1 += dy0 + dy1;
-              m2 = fmaf(dy0, yh0, fmaf(dy1, yh1, m2));
-              pw[t] = pack_bf16(d0 * yh0, d1 * yh1);
-              dpk[q * 4 + t] = gw[t];
-            }
-            if (valid) pws[cg * 4 + q] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          for (int j = 0; j < 16; ++j) {
+            const int col = cg * 32 + 2 * j;
+            const float yh0 = (__uint_as_float(v[2 * j]) + b2[col] - mean) * rstd;
+            const float yh1 = (__uint_as_float(v[2 * j + 1]) + b2[col + 1] - mean) * rstd;
+            const float d0 = bf16_lo(gw[j]), d1 = bf16_hi(gw[j]);
+            const float dy0 = d0 * gam[col], dy1 = d1 * gam[col + 1];
+            m1 += dy0 + dy1;
+            m2 = fmaf(dy0, yh0, fmaf(dy1, yh1, m2));
+            pw[j] = pack_bf16(d0 * yh0, d1 * yh1);
           }
-          tmem_st8(aop + cg * 16, dpk);          // park dO (bf16) in the free A-operand columns
-          tmem_st8(aop + cg * 16 + 8, dpk + 8);
+          if (valid) { stg256(pws + cg * 32, pw); stg256(pws + cg * 32 + 16, pw + 8); }
+          tmem_st8(aop + cg * 16, gw);           // park dO (bf16) in the free A-operand columns
+          tmem_st8(aop + cg * 16 + 8, gw + 8);
         }
         tmem_st_wait();
         m1 *= (1.0f / kD);
         m2 *= (1.0f / kD);
-        uint4* g2ws = reinterpret_cast<uint4*>(bw.G2 + lrow * kD);
+        __nv_bfloat16* g2ws = bw.G2 + lrow * kD;
 #pragma unroll 1
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32], dpk[16];
           tmem_ld32(acc + cg * 32, v);
-          // 16 packed dO words of this column group
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                       : "=r"(dpk[0]), "=r"(dpk[1]), "=r"(dpk[2]), "=r"(dpk[3]), "=r"(dpk[4]), "=r"(dpk[5]), "=r"(dpk[6]), "=r"(dpk[7]),
-                         "=r"(dpk[8]), "=r"(dpk[9]), "=r"(dpk[10]), "=r"(dpk[11]), "=r"(dpk[12]), "=r"(dpk[13]), "=r"(dpk[14]), "=r"(dpk[15])
-                       : "r"(aop + cg * 16) : "memory");
+          tmem_ld16(aop + cg * 16, dpk);
           tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
@@ -431,17 +482,15 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           }
           tmem_st8(aop + cg * 16, o);
           tmem_st8(aop + cg * 16 + 8, o + 8);
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) g2ws[cg * 4 + q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          }
+          if (valid) { stg256(g2ws + cg * 32, o); stg256(g2ws + cg * 32 + 16, o + 8); }
         }
         tmem_st_wait();
         signal_done();
         // ---- dH2' = (dY W2) * [H2 > 0] ; dH1' = (dH2' W1) * [H1 > 0] ------------------------------
+#pragma unroll 1
         for (int layer = 1; layer >= 0; --layer) {
           wait_acc();
-          uint4* gws = reinterpret_cast<uint4*>((layer == 1 ? bw.G1 : bw.G0) + lrow * kD);
+          __nv_bfloat16* gws = (layer == 1 ? bw.G1 : bw.G0) + lrow * kD;
 #pragma unroll 1
           for (int cg = 0; cg < 4; ++cg) {
             uint32_t v[32];
@@ -457,10 +506,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
             }
             tmem_st8(aop + cg * 16, o);
             tmem_st8(aop + cg * 16 + 8, o + 8);
-            if (valid) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) gws[cg * 4 + q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            }
+            if (valid) { stg256(gws + cg * 32, o); stg256(gws + cg * 32 + 16, o + 8); }
           }
           tmem_st_wait();
           signal_done();
@@ -469,8 +515,8 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
         for (int c = 0; c < nch; ++c) {
           wait_acc();
           __nv_bfloat16* dst = bw.grad_chunk[c];
-          if (dst != nullptr) {
-            uint4* dp = reinterpret_cast<uint4*>(dst + (valid ? grow : 0) * kD);
+          if (dst != nullptr) {                       // warp-uniform: tcgen05.ld is a warp-collective
+            __nv_bfloat16* dp = dst + (valid ? grow : 0) * kD;
             const bool add_resid = (c == bw.resid_chunk);
 #pragma unroll 1
             for (int cg = 0; cg < 4; ++cg) {
@@ -478,17 +524,15 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
               tmem_ld32(acc + cg * 32, v);
               tmem_ld_wait();
               if (valid) {
+                uint32_t gw[16], ow[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4 gv = make_uint4(0, 0, 0, 0);
-                  if (add_resid) gv = __ldg(gop + cg * 4 + q);
-                  const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-                  uint32_t ow[4];
+                for (int j = 0; j < 16; ++j) gw[j] = 0u;
+                if (add_resid) { ldg256(gop + cg * 32, gw); ldg256(gop + cg * 32 + 16, gw + 8); }
 #pragma unroll
-                  for (int t = 0; t < 4; ++t)
-                    ow[t] = pack_bf16(__uint_as_float(v[q * 8 + t * 2]) + bf16_lo(gw[t]), __uint_as_float(v[q * 8 + t * 2 + 1]) + bf16_hi(gw[t]));
-                  dp[cg * 4 + q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
+                for (int j = 0; j < 16; ++j)
+                  ow[j] = pack_bf16(__uint_as_float(v[2 * j]) + bf16_lo(gw[j]), __uint_as_float(v[2 * j + 1]) + bf16_hi(gw[j]));
+                stg256(dp + cg * 32, ow);
+                stg256(dp + cg * 32 + 16, ow + 8);
               }
             }
           }
@@ -553,7 +597,7 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
     if (tid < kWgStages) mbar_arrive(&bars[3 + tid]);     // ring starts empty
     for (int64_t st = 0; st < n_steps; ++st) {
       const int stage = int(st % kWgStages);
-      mbar_wait(&bars[3 + stage], uint32_t(st / kWgStages) & 1);
+      mbar_wait(&bars[3 + stage], uint32_t(st / kWgStages) & 1, 10);
       const int64_t row0 = r_beg + st * kWgRows;
       const uint32_t saddr = sbase + stage * kWgStageBytes;
       for (int t = 0; t < n_tiles; ++t) {
@@ -563,28 +607,39 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
         if (group == 0) src = t == 0 ? wa.G2 : t == 1 ? wa.H2 : t == 2 ? wa.G1 : wa.H1;
         else if (t == 0) src = wa.G0;
         else { src = static_cast<const __nv_bfloat16*>(ch.src[c_first + t - 1]); idx = ch.idx[c_first + t - 1]; roff = ch.row_offset[c_first + t - 1]; }
+        const int c16 = tid & 15, rbase = tid >> 4;       // piece c16 of rows rbase + 8 j
+        int64_t srow[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int q = tid + 128 * j;           // 1024 16-byte pieces
-          const int row = q >> 4, c16 = q & 15;
-          const int64_t grow = row0 + row;
-          const bool valid = grow < r_end;
-          int64_t srow = 0;
-          if (valid) srow = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
-          cp_async16_zfill(saddr + t * kWgTileBytes + (c16 >> 3) * 8192 + sw128_chunk(row, c16 & 7), src + srow * kD + c16 * 8, valid);
+          const int64_t grow = row0 + rbase + 8 * j;
+          srow[j] = -1;
+          if (grow < r_end) srow[j] = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool valid = srow[j] >= 0;
+          cp_async16_zfill(saddr + t * kWgTileBytes + (c16 >> 3) * 8192 + sw128_chunk(rbase + 8 * j, c16 & 7),
+                           src + (valid ? srow[j] : 0) * kD + c16 * 8, valid);
         }
       }
       cp_async_commit();
-      cp_async_wait<0>();
-      fence_async_smem();
-      mbar_arrive(&bars[stage]);
+      // keep up to three stages of loads in flight: publish stage st-2 once its group has landed
+      if (st >= 2) {
+        cp_async_wait<2>();
+        fence_async_smem();
+        mbar_arrive(&bars[int((st - 2) % kWgStages)]);
+      }
     }
+    cp_async_wait<0>();
+    fence_async_smem();
+    if (n_steps >= 2) mbar_arrive(&bars[int((n_steps - 2) % kWgStages)]);
+    if (n_steps >= 1) mbar_arrive(&bars[int((n_steps - 1) % kWgStages)]);
   } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);     // both operands MN-major
       for (int64_t st = 0; st < n_steps; ++st) {
         const int stage = int(st % kWgStages);
-        mbar_wait(&bars[stage], uint32_t(st / kWgStages) & 1);
+        mbar_wait(&bars[stage], uint32_t(st / kWgStages) & 1, 11);
         fence_after_sync();
         const uint32_t saddr = sbase + stage * kWgStageBytes;
         for (int o = 0; o < n_out; ++o) {
@@ -605,7 +660,7 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     (void)ew;
     if (n_steps > 0) {
-      mbar_wait(&bars[6], 0);
+      mbar_wait(&bars[6], 0, 12);
       fence_after_sync();
     }
     const int o_row = quarter * 32 + lane;        // output row (= "out" feature of the weight)
@@ -660,9 +715,13 @@ static int sm_count() {
   return n;
 }
 
+uint32_t* debug_buffer_device();   // cabi.cu: host-mapped words, readable after a device trap
+
 static int configure_kernels() {
   static bool configured = false;
   if (!configured) {
+    uint32_t* dbg = debug_buffer_device();
+    HGN_CUDA_OK(cudaMemcpyToSymbol(tc05::g_debug_words, &dbg, sizeof(dbg)));
     HGN_CUDA_OK(cudaFuncSetAttribute(mlp_tile_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     HGN_CUDA_OK(cudaFuncSetAttribute(mlp_tile_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     HGN_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -675,7 +734,7 @@ int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const
                    cudaStream_t st) {
   const int nch = ch->n_chunks;
   const bool resident = nch <= kMaxResidentChunks;
-  const TileSmem S(nch, resident);
+  const TileSmem S(nch, resident, false);
   if (int rc = configure_kernels()) return rc;
   const int64_t tiles = ceil_div(rows, kTile);
   const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
@@ -724,7 +783,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
                     float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const int nch = ch->n_chunks;
   const bool resident = nch <= kMaxResidentChunks;
-  const TileSmem S(nch, resident);
+  const TileSmem S(nch, resident, true);
   const BwdLayoutTc L = bwd_layout_tc(rows, nch);
   if (workspace_bytes < L.total) { set_error("mlp_backward(bf16): workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
   if (int rc = configure_kernels()) return rc;

@@ -122,12 +122,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking poll
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Bounded wait: a lost arrive must end in a trap (an error the host sees), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+// Host-mapped diagnostics buffer (set per translation unit by set_debug_buffer): a stalled wait records
+// {magic, tag, block, thread, parity, extra...} where the host can still read it after the trap.
+static __device__ uint32_t* g_debug_words = nullptr;
+__device__ __forceinline__ void debug_record(uint32_t tag, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+  uint32_t* w = g_debug_words;
+  if (w != nullptr && atomicCAS(w, 0u, 0xB200DEADu) == 0u) {
+    w[1] = tag; w[2] = blockIdx.x; w[3] = threadIdx.x; w[4] = a; w[5] = b; w[6] = c; w[7] = d; w[8] = e; w[9] = f;
+    __threadfence_system();
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  for (uint32_t spin = 0; spin < (1u << 23); ++spin) {
     if (mbar_try_wait(bar, parity)) return;
   }
-  printf("hgn_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  debug_record(uint32_t(tag), parity, 0, 0, 0, 0, 0);
   __trap();
 }
 
@@ -142,6 +159,22 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// ---- 256-bit global accesses (sm_100): one full 32-byte sector per lane -----------------------------
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
 
 // ---- small helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
