@@ -21,6 +21,8 @@
 // Weight-gradient kernel: dW = G^T Z as tcgen05 GEMMs with BOTH operands MN-major, i.e. the row-major
 // [rows,128] activation / gradient tiles are consumed exactly as they sit in memory; accumulators stay in
 // TMEM over a CTA's whole row range; per-CTA partials are reduced in a fixed order afterwards.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -109,6 +111,7 @@ struct BwdArgs {
   __nv_bfloat16* grad_chunk[HGN_MAX_CHUNKS];
   __nv_bfloat16 *H1, *H2, *P, *G2, *G1, *G0;   // slab workspaces [rows,128]
   int resid_chunk;
+  int ablate;   // development switches (HGN_TC_ABLATE): 1 skip workspace stores, 2 skip dX stores, 4 skip dO loads
 };
 
 // 8 MMAs: acc (+)= A[128 x 128] * B^T with A in TMEM (bf16 pairs) and B = a resident 128x128 weight block
@@ -315,7 +318,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
         }
       }
       if (!progressed) {
-        __nanosleep(20);
+        if (!(bw.ablate & 8)) __nanosleep(20);
         if (++idle > (1u << 22)) {
           if (lane == 0)
             debug_record(900u + uint32_t(kBwd), uint32_t(t_l0) | (uint32_t(c_l0) << 16), uint32_t(g), uint32_t(done) | (uint32_t(my_tiles) << 16),
@@ -378,7 +381,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           tmem_st8(aop + cg * 16 + 8, h + 8);
           if (kBwd) {
             if (layer == 0) mask1[cg] = m; else mask2[cg] = m;
-            if (valid) { stg256(hws + cg * 32, h); stg256(hws + cg * 32 + 16, h + 8); }
+            if (valid && !(bw.ablate & 1)) { stg256(hws + cg * 32, h); stg256(hws + cg * 32 + 16, h + 8); }
           }
         }
         tmem_st_wait();
@@ -444,7 +447,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           uint32_t gw[16], pw[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) gw[j] = 0u;
-          if (valid) { ldg256(gop + cg * 32, gw); ldg256(gop + cg * 32 + 16, gw + 8); }
+          if (valid && !(bw.ablate & 4)) { ldg256(gop + cg * 32, gw); ldg256(gop + cg * 32 + 16, gw + 8); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = cg * 32 + 2 * j;
@@ -456,7 +459,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
             m2 = fmaf(dy0, yh0, fmaf(dy1, yh1, m2));
             pw[j] = pack_bf16(d0 * yh0, d1 * yh1);
           }
-          if (valid) { stg256(pws + cg * 32, pw); stg256(pws + cg * 32 + 16, pw + 8); }
+          if (valid && !(bw.ablate & 1)) { stg256(pws + cg * 32, pw); stg256(pws + cg * 32 + 16, pw + 8); }
           tmem_st8(aop + cg * 16, gw);           // park dO (bf16) in the free A-operand columns
           tmem_st8(aop + cg * 16 + 8, gw + 8);
         }
@@ -482,7 +485,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           }
           tmem_st8(aop + cg * 16, o);
           tmem_st8(aop + cg * 16 + 8, o + 8);
-          if (valid) { stg256(g2ws + cg * 32, o); stg256(g2ws + cg * 32 + 16, o + 8); }
+          if (valid && !(bw.ablate & 1)) { stg256(g2ws + cg * 32, o); stg256(g2ws + cg * 32 + 16, o + 8); }
         }
         tmem_st_wait();
         signal_done();
@@ -506,7 +509,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
             }
             tmem_st8(aop + cg * 16, o);
             tmem_st8(aop + cg * 16 + 8, o + 8);
-            if (valid) { stg256(gws + cg * 32, o); stg256(gws + cg * 32 + 16, o + 8); }
+            if (valid && !(bw.ablate & 1)) { stg256(gws + cg * 32, o); stg256(gws + cg * 32 + 16, o + 8); }
           }
           tmem_st_wait();
           signal_done();
@@ -531,8 +534,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                   ow[j] = pack_bf16(__uint_as_float(v[2 * j]) + bf16_lo(gw[j]), __uint_as_float(v[2 * j + 1]) + bf16_hi(gw[j]));
-                stg256(dp + cg * 32, ow);
-                stg256(dp + cg * 32 + 16, ow + 8);
+                if (!(bw.ablate & 2)) { stg256(dp + cg * 32, ow); stg256(dp + cg * 32 + 16, ow + 8); }
               }
             }
           }
@@ -595,40 +597,67 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
   if (warp < 4) {
     // ---- producers: dense rows (and gathered X chunks) -> MN-major operand tiles ------------------------
     if (tid < kWgStages) mbar_arrive(&bars[3 + tid]);     // ring starts empty
+    const int c16 = tid & 15, rbase = tid >> 4;           // this thread copies piece c16 of rows rbase + 8 j
+    // source rows of the gathered X tiles, fetched one stage ahead of the copies that use them
+    auto fetch_rows = [&](int64_t st, int32_t (&srow)[3][8]) {
+      if (group == 0) return;
+      const int64_t row0 = r_beg + st * kWgRows;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        if (t >= n_out) break;
+        const int32_t* idx = ch.idx[c_first + t];
+        const int64_t roff = ch.row_offset[c_first + t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t grow = row0 + rbase + 8 * j;
+          srow[t][j] = -1;
+          if (grow < r_end) srow[t][j] = idx ? __ldg(idx + grow) : int32_t(grow + roff);
+        }
+      }
+    };
+    int32_t cur[3][8], nxt[3][8];
+    if (n_steps > 0) fetch_rows(0, cur);
     for (int64_t st = 0; st < n_steps; ++st) {
       const int stage = int(st % kWgStages);
       mbar_wait(&bars[3 + stage], uint32_t(st / kWgStages) & 1, 10);
       const int64_t row0 = r_beg + st * kWgRows;
-      const uint32_t saddr = sbase + stage * kWgStageBytes;
-      for (int t = 0; t < n_tiles; ++t) {
-        const __nv_bfloat16* src;
-        const int32_t* idx = nullptr;
-        int64_t roff = -slab0;                 // workspace tiles are slab-local
-        if (group == 0) src = t == 0 ? wa.G2 : t == 1 ? wa.H2 : t == 2 ? wa.G1 : wa.H1;
-        else if (t == 0) src = wa.G0;
-        else { src = static_cast<const __nv_bfloat16*>(ch.src[c_first + t - 1]); idx = ch.idx[c_first + t - 1]; roff = ch.row_offset[c_first + t - 1]; }
-        const int c16 = tid & 15, rbase = tid >> 4;       // piece c16 of rows rbase + 8 j
-        int64_t srow[8];
+      const uint32_t saddr = sbase + stage * kWgStageBytes + (c16 >> 3) * 8192;
+      // dense workspace tiles (slab-local rows)
+      const int n_dense = group == 0 ? 4 : 1;
+      for (int t = 0; t < n_dense; ++t) {
+        const __nv_bfloat16* src = group == 0 ? (t == 0 ? wa.G2 : t == 1 ? wa.H2 : t == 2 ? wa.G1 : wa.H1) : wa.G0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int64_t grow = row0 + rbase + 8 * j;
-          srow[j] = -1;
-          if (grow < r_end) srow[j] = idx ? int64_t(__ldg(idx + grow)) : grow + roff;
+          const bool valid = grow < r_end;
+          cp_async16_zfill(saddr + t * kWgTileBytes + sw128_chunk(rbase + 8 * j, c16 & 7), src + (valid ? grow - slab0 : 0) * kD + c16 * 8, valid);
         }
+      }
+      if (group != 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool valid = srow[j] >= 0;
-          cp_async16_zfill(saddr + t * kWgTileBytes + (c16 >> 3) * 8192 + sw128_chunk(rbase + 8 * j, c16 & 7),
-                           src + (valid ? srow[j] : 0) * kD + c16 * 8, valid);
+        for (int t = 0; t < 3; ++t) {
+          if (t >= n_out) break;
+          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(ch.src[c_first + t]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool valid = cur[t][j] >= 0;
+            cp_async16_zfill(saddr + (1 + t) * kWgTileBytes + sw128_chunk(rbase + 8 * j, c16 & 7),
+                             src + int64_t(valid ? cur[t][j] : 0) * kD + c16 * 8, valid);
+          }
         }
       }
       cp_async_commit();
+      if (st + 1 < n_steps) fetch_rows(st + 1, nxt);
       // keep up to three stages of loads in flight: publish stage st-2 once its group has landed
       if (st >= 2) {
         cp_async_wait<2>();
         fence_async_smem();
         mbar_arrive(&bars[int((st - 2) % kWgStages)]);
       }
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[t][j] = nxt[t][j];
     }
     cp_async_wait<0>();
     fence_async_smem();
@@ -739,6 +768,7 @@ int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const
   const int64_t tiles = ceil_div(rows, kTile);
   const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
   BwdArgs none{};
+  { const char* ab = getenv("HGN_TC_ABLATE"); none.ablate = ab ? atoi(ab) : 0; }
   HGN_TIMED("mlp_tile_tc_fwd", st);
   mlp_tile_tc_kernel<false><<<grid, kTileThreads, S.total, st>>>(rows, tiles, 0, *ch, static_cast<const uint8_t*>(packed), resident ? 1 : 0,
                                                                  static_cast<const __nv_bfloat16*>(resid), resid_off,
@@ -794,6 +824,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
   bw.H1 = (__nv_bfloat16*)(ws + L.act[0]); bw.H2 = (__nv_bfloat16*)(ws + L.act[1]); bw.P = (__nv_bfloat16*)(ws + L.act[2]);
   bw.G2 = (__nv_bfloat16*)(ws + L.act[3]); bw.G1 = (__nv_bfloat16*)(ws + L.act[4]); bw.G0 = (__nv_bfloat16*)(ws + L.act[5]);
   bw.resid_chunk = resid_chunk;
+  { const char* ab = getenv("HGN_TC_ABLATE"); bw.ablate = ab ? atoi(ab) : 0; }
   float* partial = (float*)(ws + L.partial);
   float* vec_ws = (float*)(ws + L.vec_partial);
   float* vec_tmp = vec_ws + ceil_div(L.slab_rows, 2048) * kD;   // 5 x 128 staging for per-slab column sums
@@ -817,7 +848,8 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
     wa.accumulate = pass > 0;
     dim3 grid(unsigned(L.parts), unsigned(L.groups));
     { HGN_TIMED("mlp_wgrad_tc", st);
-    mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(rows, slab0, L.slab_rows, L.rows_per_part, *ch, wa);
+    const int64_t rpp = ceil_div(ceil_div(this_rows > 0 ? this_rows : 1, L.parts), kWgRows) * kWgRows;
+    mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(rows, slab0, L.slab_rows, rpp, *ch, wa);
     }
     HGN_LAUNCH_OK("mlp_wgrad_tc");
     // bias / LayerNorm vector gradients: column sums of G2, G1, G0, P and grad_out over this slab

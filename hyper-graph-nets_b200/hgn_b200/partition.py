@@ -1,0 +1,328 @@
+"""Edge-cut graph partitioning with a one-ring halo of sender latents.
+
+The reference is single-device (no ``torch.distributed`` anywhere), so this is new functionality whose
+parity contract is "P-rank result == 1-rank result".  Scheme:
+
+* nodes are split into P parts; every directed edge belongs to the OWNER OF ITS RECEIVER, so the
+  edge->node aggregation and the node update are rank-local and edge latents never move;
+* the only remote data are sender latents of cut edges: each rank keeps them as GHOST rows.  A rank's
+  node list is ``[owned | ghosts]`` -- exactly the reference's ``node_features = [mesh, hyper]`` row
+  concatenation (util.py:11-12, hierarchical_connector.py:37), so the unmodified ``GraphNet`` block
+  updates the owned rows (list slot 0) and leaves the ghosts (slot 1) alone;
+* before every block the owners send their boundary rows to the ranks that hold them as ghosts
+  (``HaloExchange``: pack kernel -> grouped NCCL send/recv over NVLink -> ghosts land contiguously, ordered by
+  owner, so no unpack is needed); in the backward pass ghost gradients travel back and are added at the
+  owner peer by peer in rank order (deterministic);
+* weight gradients are summed with one all-reduce after the backward pass.
+
+Nothing here does arithmetic on latents besides the pack / scatter-add row kernels of ``libhgn_b200.so``
+(CPU tensors use torch indexing instead, which is how the world_size-2 gloo tests exercise this logic).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+
+# ------------------------------------------------------------------------------------------------------
+# partition plan (pure index bookkeeping, bit-exact, CPU)
+# ------------------------------------------------------------------------------------------------------
+@dataclass
+class LocalGraph:
+    rank: int
+    world: int
+    owned: torch.Tensor            # [n_own]   global ids of the owned nodes (ascending)
+    ghosts: torch.Tensor           # [n_ghost] global ids of the ghost nodes, sorted by (owner, id)
+    ghost_splits: List[int]        # ghosts received from each rank (sums to n_ghost)
+    send_index: torch.Tensor       # [n_send]  LOCAL owned indices to send, grouped by destination rank
+    send_splits: List[int]         # rows sent to each rank
+    edge_ids: torch.Tensor         # [e_loc]   global ids of the local edges (ascending -> original order kept)
+    senders: torch.Tensor          # [e_loc]   local sender index into [owned | ghosts]
+    receivers: torch.Tensor        # [e_loc]   local receiver index (always < n_own)
+
+    @property
+    def n_own(self) -> int:
+        return int(self.owned.numel())
+
+    @property
+    def n_ghost(self) -> int:
+        return int(self.ghosts.numel())
+
+
+def block_partition(num_nodes: int, world: int) -> torch.Tensor:
+    """Contiguous id ranges (row slabs of a row-major grid mesh): part id per node."""
+    bounds = [(num_nodes * p) // world for p in range(world + 1)]
+    part = torch.empty(num_nodes, dtype=torch.int64)
+    for p in range(world):
+        part[bounds[p]:bounds[p + 1]] = p
+    return part
+
+
+def coordinate_bisection(pos: torch.Tensor, world: int) -> torch.Tensor:
+    """Recursive coordinate bisection of node positions into ``world`` (power of two) parts."""
+    n = pos.shape[0]
+    part = torch.zeros(n, dtype=torch.int64)
+    groups = [torch.arange(n)]
+    while len(groups) < world:
+        nxt = []
+        for ids in groups:
+            p = pos[ids]
+            axis = int(torch.argmax(p.max(0).values - p.min(0).values))
+            order = torch.argsort(p[:, axis], stable=True)
+            half = ids.numel() // 2
+            nxt += [ids[order[:half]], ids[order[half:]]]
+        groups = nxt
+    for k, ids in enumerate(groups):
+        part[ids] = k
+    return part
+
+
+def build_local_graph(senders: torch.Tensor, receivers: torch.Tensor, part: torch.Tensor, rank: int, world: int) -> LocalGraph:
+    """Rank ``rank``'s share of a directed edge list under the receiver-owner rule."""
+    senders, receivers, part = senders.cpu(), receivers.cpu(), part.cpu()
+    owned = torch.nonzero(part == rank).flatten()
+    edge_ids = torch.nonzero(part[receivers] == rank).flatten()
+    s_glob, r_glob = senders[edge_ids], receivers[edge_ids]
+    # ghosts: senders of local edges owned elsewhere, ordered by (owner, global id)
+    remote = torch.unique(s_glob[part[s_glob] != rank])
+    order = torch.argsort(part[remote] * (part.numel() + 1) + remote)
+    ghosts = remote[order]
+    ghost_splits = torch.bincount(part[ghosts], minlength=world).tolist()
+    # global -> local id
+    local_of = torch.full((part.numel(),), -1, dtype=torch.int64)
+    local_of[owned] = torch.arange(owned.numel())
+    local_of[ghosts] = owned.numel() + torch.arange(ghosts.numel())
+    # what do the other ranks need from me?  (their ghost lists restricted to my nodes, same ordering rule)
+    send_lists = []
+    for q in range(world):
+        if q == rank:
+            send_lists.append(torch.empty(0, dtype=torch.int64))
+            continue
+        q_edges = part[receivers] == q
+        need = torch.unique(senders[q_edges & (part[senders] == rank)])   # ascending global id == q's ghost order
+        send_lists.append(local_of[need])
+    return LocalGraph(rank=rank, world=world, owned=owned, ghosts=ghosts, ghost_splits=ghost_splits,
+                      send_index=torch.cat(send_lists), send_splits=[int(t.numel()) for t in send_lists],
+                      edge_ids=edge_ids, senders=local_of[s_glob], receivers=local_of[r_glob])
+
+
+# ------------------------------------------------------------------------------------------------------
+# halo exchange
+# ------------------------------------------------------------------------------------------------------
+def _gather_rows(src: torch.Tensor, index: torch.Tensor, index32: Optional[torch.Tensor]) -> torch.Tensor:
+    if not src.is_cuda:
+        return src.index_select(0, index)
+    lib = _cabi.load()
+    out = torch.empty((index.numel(), src.shape[1]), dtype=src.dtype, device=src.device)
+    if index.numel():
+        _cabi.check(lib.hgn_rows_gather(_cabi.dtype_code(src.dtype), src.data_ptr(), index32.data_ptr(), index.numel(), src.shape[1],
+                                        out.data_ptr(), _cabi.stream_ptr()), "hgn_rows_gather")
+    return out
+
+
+def _scatter_add_rows(dst: torch.Tensor, rows: torch.Tensor, index: torch.Tensor, index32: Optional[torch.Tensor]) -> None:
+    """dst[index[i]] += rows[i]; ``index`` has no duplicates (one peer at a time)."""
+    if not rows.numel():
+        return
+    if not dst.is_cuda:
+        dst.index_add_(0, index, rows)
+        return
+    lib = _cabi.load()
+    _cabi.check(lib.hgn_rows_scatter(_cabi.dtype_code(dst.dtype), rows.data_ptr(), index32.data_ptr(), index.numel(), dst.shape[1],
+                                     dst.data_ptr(), 1, _cabi.stream_ptr()), "hgn_rows_scatter")
+
+
+def _exchange(send: torch.Tensor, send_splits: Sequence[int], recv_splits: Sequence[int], group) -> torch.Tensor:
+    """All-to-all-v of row blocks with grouped point-to-point operations (NCCL: one fused launch over NVLink)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    recv = torch.empty((sum(recv_splits), send.shape[1]), dtype=send.dtype, device=send.device)
+    ops, so, ro = [], 0, 0
+    for q in range(world):
+        if q != rank and recv_splits[q]:
+            ops.append(dist.P2POp(dist.irecv, recv[ro:ro + recv_splits[q]], q, group))
+        ro += recv_splits[q]
+    for q in range(world):
+        if q != rank and send_splits[q]:
+            ops.append(dist.P2POp(dist.isend, send[so:so + send_splits[q]].contiguous(), q, group))
+        so += send_splits[q]
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    return recv
+
+
+class HaloPlan:
+    """Device-side copy of a ``LocalGraph``'s exchange lists."""
+
+    def __init__(self, lg: LocalGraph, device, group=None):
+        self.lg = lg
+        self.group = group
+        self.send_index = lg.send_index.to(device)
+        self.send_index32 = self.send_index.to(torch.int32) if torch.device(device).type == "cuda" else None
+        self.send_splits = list(lg.send_splits)
+        self.ghost_splits = list(lg.ghost_splits)
+        self.peer_offsets = [0]
+        for n in self.send_splits:
+            self.peer_offsets.append(self.peer_offsets[-1] + n)
+
+
+class _HaloExchange(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, owned: torch.Tensor, plan: HaloPlan):
+        ctx.plan = plan
+        ctx.n_own = owned.shape[0]
+        packed = _gather_rows(owned.contiguous(), plan.send_index, plan.send_index32)
+        return _exchange(packed, plan.send_splits, plan.ghost_splits, plan.group)
+
+    @staticmethod
+    def backward(ctx, grad_ghosts: torch.Tensor):
+        plan: HaloPlan = ctx.plan
+        back = _exchange(grad_ghosts.contiguous(), plan.ghost_splits, plan.send_splits, plan.group)
+        grad_owned = torch.zeros((ctx.n_own, grad_ghosts.shape[1]), dtype=grad_ghosts.dtype, device=grad_ghosts.device)
+        for q in range(len(plan.send_splits)):          # peers in rank order: fixed summation order
+            lo, hi = plan.peer_offsets[q], plan.peer_offsets[q + 1]
+            if hi > lo:
+                idx32 = plan.send_index32[lo:hi] if plan.send_index32 is not None else None
+                _scatter_add_rows(grad_owned, back[lo:hi], plan.send_index[lo:hi], idx32)
+        return grad_owned, None
+
+
+def halo_exchange(owned: torch.Tensor, plan: HaloPlan) -> torch.Tensor:
+    """Ghost rows ``[n_ghost, D]`` (ordered by owner rank) holding the owners' current latents."""
+    return _HaloExchange.apply(owned, plan)
+
+
+class PartitionedProcessor(torch.nn.Module):
+    """Runs a (reference-API) ``Processor`` on one rank's share of the graph: ghosts are refreshed before
+    every block; the block itself is unchanged (it sees ``[owned | ghosts]`` as ``[mesh | hyper]`` rows)."""
+
+    def __init__(self, processor: torch.nn.Module, plan: HaloPlan):
+        super().__init__()
+        self.processor = processor
+        self.plan = plan
+
+    def forward(self, owned: torch.Tensor, edge_sets):
+        from .util import MultiGraph
+        precision = getattr(self.processor, "precision", None)
+        in_dtype = owned.dtype
+        if precision == "bf16":
+            owned = owned.to(torch.bfloat16)
+            edge_sets = [es._replace(features=es.features.to(torch.bfloat16)) for es in edge_sets]
+        graph = MultiGraph([owned, None], list(edge_sets))
+        for block in self.processor.graphnet_blocks:
+            graph.node_features[1] = halo_exchange(graph.node_features[0], self.plan)
+            graph = block(graph)
+        out_nodes = graph.node_features[0].to(in_dtype)
+        return out_nodes, [es._replace(features=es.features.to(in_dtype)) for es in graph.edge_sets]
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
+    """Sum the per-rank partial weight gradients (one flat fp32 all-reduce)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU benchmark (bench.py --gpus N under torchrun)
+# ------------------------------------------------------------------------------------------------------
+def bench_partitioned(args, world, rank, dev, width, height, layers, metric, unit, peaks, clock_sampler_cls):
+    import json
+    import os
+    from . import ops, synthetic
+    from .migration.meshgraphnet import MeshGraphNet
+    from .util import EdgeSet
+
+    n = width * height
+    senders, receivers = synthetic.grid_edges_two_way(width, height)
+    e_total = senders.numel()
+    part = block_partition(n, world)
+    lg = build_local_graph(senders, receivers, part, rank, world)
+    gen = torch.Generator().manual_seed(0)
+    v0 = torch.randn(n, 128, generator=gen)[lg.owned]
+    e0 = torch.randn(e_total, 128, generator=gen)[lg.edge_ids]
+    coef = torch.randn(n, 128, generator=gen)[lg.owned].to(dev)
+    weights = synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), seed=17)
+    shell = MeshGraphNet(3, 128, 2, "sum", layers, "none", ["mesh_edges"])
+    proc = shell.processor
+    proc.load_state_dict({k[len("processor."):]: t for k, t in weights.items()})
+    proc = proc.to(dev)
+    proc.precision = "bf16"
+    plan = HaloPlan(lg, dev)
+    model = PartitionedProcessor(proc, plan)
+    params = list(proc.parameters())
+    v_dev, e_dev = v0.to(dev), e0.to(dev)
+    v_host, e_host = v0.pin_memory(), e0.pin_memory()
+    s_loc, r_loc = lg.senders.to(dev), lg.receivers.to(dev)
+    loss_host = torch.empty(1).pin_memory()
+
+    def step(v_in, e_in):
+        for p in params:
+            p.grad = None
+        v = v_in.requires_grad_(True)
+        ed = e_in.requires_grad_(True)
+        out_v, out_sets = model(v, [EdgeSet("mesh_edges", ed, s_loc, r_loc)])
+        loss = (out_v * coef).sum() + out_sets[0].features.sum() * 1e-3
+        loss.backward()
+        allreduce_gradients(proc)
+        return loss
+
+    def timed(fn, steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(v_dev.detach(), e_dev.detach())
+    launches0 = ops.launch_count
+    with clock_sampler_cls(dev.index) as clocks:
+        ms_per_step = timed(lambda: step(v_dev.detach(), e_dev.detach()), args.steps)
+    launches = ops.launch_count - launches0
+
+    def step_e2e():
+        loss = step(v_host.to(dev, non_blocking=True), e_host.to(dev, non_blocking=True))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e()
+    e2e_ms = timed(step_e2e, max(1, min(args.steps, 3)))
+    halo_rows = torch.tensor([float(lg.n_ghost)], device=dev)
+    dist.all_reduce(halo_rows, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = e_total * layers / (ms_per_step * 1e-3)
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
+            "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, processor fwd+bwd",
+                       "nodes": n, "edges": e_total, "layers": layers, "latent": 128,
+                       "partitioning": f"edge-cut, {world} row slabs, receiver-owner rule, halo of sender latents per layer "
+                                       f"(max {int(halo_rows)} ghost rows per rank), NCCL grouped send/recv, weight-gradient all-reduce",
+                       "l2_policy": "inputs larger than L2"},
+            "e2e": {"value": e_total * layers / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int((v_host.numel() + e_host.numel()) * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks.summary(),
+            "roofline": None, "cpu_baseline": None,
+        }))
+    dist.destroy_process_group()

@@ -1,0 +1,117 @@
+"""Host-side logic of the edge-cut partitioning, on CPU:
+* the partition bookkeeping is bit-exact (every edge owned once, ghosts = remote senders, send/recv lists agree);
+* a world_size-2 gloo run of the halo exchange + weight-gradient all-reduce, with the CPU oracle doing the
+  arithmetic, reproduces the single-process result (forward latents and all gradients)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import hgn_oracle as orc
+from conftest import ROOT
+from hgn_b200 import partition, synthetic
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_partition_bookkeeping_bit_exact(world):
+    w, h = 13, 11
+    s, r = synthetic.grid_edges_two_way(w, h)
+    n = w * h
+    part = partition.block_partition(n, world)
+    lgs = [partition.build_local_graph(s, r, part, p, world) for p in range(world)]
+    all_edges = torch.cat([lg.edge_ids for lg in lgs])
+    assert torch.equal(torch.sort(all_edges).values, torch.arange(s.numel()))          # each edge owned exactly once
+    assert torch.equal(torch.sort(torch.cat([lg.owned for lg in lgs])).values, torch.arange(n))
+    for lg in lgs:
+        glob = torch.cat([lg.owned, lg.ghosts])
+        assert torch.equal(glob[lg.senders], s[lg.edge_ids]) and torch.equal(glob[lg.receivers], r[lg.edge_ids])
+        assert int(lg.receivers.max()) < lg.n_own                                     # receivers are always owned
+        assert (part[lg.ghosts] != lg.rank).all() and sum(lg.ghost_splits) == lg.n_ghost
+        assert torch.equal(lg.edge_ids, torch.sort(lg.edge_ids).values)               # original edge order kept
+    for p in range(world):
+        for q in range(world):
+            if p == q:
+                continue
+            lo = sum(lgs[p].send_splits[:q])
+            sent_global = lgs[p].owned[lgs[p].send_index[lo:lo + lgs[p].send_splits[q]]]
+            glo = sum(lgs[q].ghost_splits[:p])
+            assert torch.equal(sent_global, lgs[q].ghosts[glo:glo + lgs[q].ghost_splits[p]])   # same rows, same order
+
+
+def test_coordinate_bisection_balanced():
+    pos = synthetic.cloth_frame(16, 12, 0)["mesh_pos"]
+    part = partition.coordinate_bisection(pos, 4)
+    counts = torch.bincount(part, minlength=4)
+    assert int(counts.max() - counts.min()) <= 1
+
+
+def _oracle_block(weights, prefix, nodes, ghosts, es):
+    g = orc.block_graphnet(weights, prefix, "sum", orc.MultiGraph([nodes, ghosts], [es]))
+    return g.node_features[0], g.edge_sets[0]
+
+
+def _worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w, h, layers = 9, 8, 2
+        s, r = synthetic.grid_edges_two_way(w, h)
+        n, e = w * h, s.numel()
+        weights = {k: t.clone().requires_grad_(True) for k, t in
+                   synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), 3).items()}
+        v0 = synthetic.seeded_tensor("pv", (n, 128), 2)
+        e0 = synthetic.seeded_tensor("pe", (e, 128), 2)
+        coef = synthetic.seeded_tensor("pc", (n, 128), 2)
+        lg = partition.build_local_graph(s, r, partition.block_partition(n, world), rank, world)
+        plan = partition.HaloPlan(lg, "cpu")
+        owned = v0[lg.owned].clone().requires_grad_(True)
+        edges = e0[lg.edge_ids].clone().requires_grad_(True)
+        es = orc.EdgeSet("mesh_edges", edges, lg.senders, lg.receivers)
+        nodes = owned
+        for b in range(layers):
+            ghosts = partition.halo_exchange(nodes, plan)
+            nodes, es = _oracle_block(weights, f"processor.graphnet_blocks.{b}", nodes, ghosts, es)
+        loss = (nodes * coef[lg.owned]).sum() + es.features.sum() * 1e-3
+        loss.backward()
+
+        class _Holder(torch.nn.Module):
+            def __init__(self, ws):
+                super().__init__()
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.detach()) for t in ws.values()])
+                for p, t in zip(self.ps, ws.values()):
+                    p.grad = t.grad
+        holder = _Holder(weights)
+        partition.allreduce_gradients(holder)
+        torch.save({"owned_ids": lg.owned, "edge_ids": lg.edge_ids, "nodes": nodes.detach(), "edges": es.features.detach(),
+                    "grad_v": owned.grad, "grad_e": edges.grad, "grad_w": [p.grad for p in holder.ps]},
+                   os.path.join(tmpdir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_halo_exchange_matches_single_process(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    w, h, layers = 9, 8, 2
+    s, r = synthetic.grid_edges_two_way(w, h)
+    n, e = w * h, s.numel()
+    weights = {k: t.clone().requires_grad_(True) for k, t in
+               synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), 3).items()}
+    v = synthetic.seeded_tensor("pv", (n, 128), 2).requires_grad_(True)
+    ed = synthetic.seeded_tensor("pe", (e, 128), 2).requires_grad_(True)
+    coef = synthetic.seeded_tensor("pc", (n, 128), 2)
+    out = orc.processor(weights, "sum", "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
+    ((out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3).backward()
+    parts = [torch.load(os.path.join(tmp_path, f"rank{k}.pt")) for k in range(world)]
+    for p in parts:
+        assert torch.allclose(p["nodes"], out.node_features[0].detach()[p["owned_ids"]], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(p["edges"], out.edge_sets[0].features.detach()[p["edge_ids"]], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(p["grad_v"], v.grad[p["owned_ids"]], rtol=1e-4, atol=1e-5)     # includes ghost gradients returned
+        assert torch.allclose(p["grad_e"], ed.grad[p["edge_ids"]], rtol=1e-4, atol=1e-5)
+        for g, ref in zip(p["grad_w"], weights.values()):
+            assert torch.allclose(g, ref.grad, rtol=1e-4, atol=1e-4)                          # identical on both ranks after all-reduce
