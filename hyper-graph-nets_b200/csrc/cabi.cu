@@ -83,6 +83,19 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
                     float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
                     void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// projected edge update (edge_tc.cu)
+int edge_project_forward_tc(int64_t num_nodes, const void* v, const void* packed, void* proj_s, void* proj_r, cudaStream_t st);
+size_t edge_project_backward_workspace_tc(int64_t num_nodes);
+int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
+                             float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
+                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st);
+size_t edge_update_backward_workspace_tc(int64_t num_edges);
+int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
+                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
+                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
+                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 static int check_chunks(const hgn_chunks* ch, const char* who) {
   HGN_CHECK_ARG(ch != nullptr, "%s: chunks is NULL", who);
   HGN_CHECK_ARG(ch->n_chunks >= 1 && ch->n_chunks <= HGN_MAX_CHUNKS, "%s: n_chunks=%d outside [1,%d]", who, ch->n_chunks, HGN_MAX_CHUNKS);
@@ -158,6 +171,69 @@ extern "C" int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunk
                            grad_gamma, grad_beta, workspace, workspace_bytes, st);
   set_error("mlp_backward: unknown dtype %d", dtype);
   return HGN_ERR_INVALID_ARGUMENT;
+}
+
+#define HGN_BF16_ONLY(who)                                                                                   \
+  do {                                                                                                        \
+    if (dtype != HGN_BF16) {                                                                                  \
+      set_error("%s: only HGN_BF16 is implemented (fp32 parity mode uses hgn_mlp_*)", who);                    \
+      return HGN_ERR_UNSUPPORTED;                                                                             \
+    }                                                                                                         \
+  } while (0)
+
+extern "C" int hgn_edge_project_forward(int dtype, int64_t num_nodes, const void* v, const void* packed, void* proj_s, void* proj_r,
+                                        void* stream) {
+  HGN_BF16_ONLY("edge_project_forward");
+  HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "edge_project_forward: num_nodes=%lld", (long long)num_nodes);
+  if (num_nodes == 0) return HGN_OK;
+  HGN_CHECK_ARG(v && packed && proj_s && proj_r, "edge_project_forward: null pointer");
+  return edge_project_forward_tc(num_nodes, v, packed, proj_s, proj_r, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t num_nodes) {
+  if (dtype != HGN_BF16 || num_nodes < 0) return 0;
+  return edge_project_backward_workspace_tc(num_nodes);
+}
+
+extern "C" int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed, const void* grad_s,
+                                         const void* grad_r, void* grad_v, float* grad_W0, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  HGN_BF16_ONLY("edge_project_backward");
+  HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "edge_project_backward: num_nodes=%lld", (long long)num_nodes);
+  HGN_CHECK_ARG(packed && grad_W0 && workspace, "edge_project_backward: null pointer");
+  HGN_CHECK_ARG(num_nodes == 0 || (v && grad_s && grad_r && grad_v), "edge_project_backward: null pointer");
+  return edge_project_backward_tc(num_nodes, v, packed, grad_s, grad_r, grad_v, grad_W0, workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
+                                       const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* stream) {
+  HGN_BF16_ONLY("edge_update_forward");
+  HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_forward: num_edges=%lld", (long long)num_edges);
+  if (num_edges == 0) return HGN_OK;
+  HGN_CHECK_ARG(edge && proj_s && proj_r && senders && receivers && packed && out, "edge_update_forward: null pointer");
+  return edge_update_forward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges) {
+  if (dtype != HGN_BF16 || num_edges < 0) return 0;
+  return edge_update_backward_workspace_tc(num_edges);
+}
+
+extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
+                                        const int32_t* senders, const int32_t* receivers, const void* packed, const void* grad_out,
+                                        const void* grad_agg, void* grad_edge, void* grad_pre0, float* grad_W0, float* grad_b0,
+                                        float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma,
+                                        float* grad_beta, void* workspace, size_t workspace_bytes, void* stream) {
+  HGN_BF16_ONLY("edge_update_backward");
+  HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_backward: num_edges=%lld", (long long)num_edges);
+  HGN_CHECK_ARG(packed && workspace && grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta,
+                "edge_update_backward: null pointer");
+  HGN_CHECK_ARG(num_edges == 0 || (edge && proj_s && proj_r && senders && receivers && grad_edge && grad_pre0),
+                "edge_update_backward: null pointer");
+  return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, grad_out, grad_agg, grad_edge, grad_pre0,
+                                 grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hgn_profile_enable(int on) { g_profile_on = on != 0; return HGN_OK; }

@@ -1,0 +1,780 @@
+// bf16 tcgen05 "projected" edge update (HGN_BF16 only) -- the per-layer hot kernel of the processor.
+//
+// Reference arithmetic (src/migration/graphnet.py:22-32):  e' = e + LN(MLP([v[s] | v[r] | e])).
+// The first linear is split by input block,  W0 = [Ws | Wr | We]  (columns 0:128 | 128:256 | 256:384):
+//     pre0_e = Ws v[s_e] + Wr v[r_e] + We e_e + b0 = Ps[s_e] + Pr[r_e] + We e_e + b0,     Ps = v Ws^T, Pr = v Wr^T
+// The two node-side products are computed once per NODE (proj kernel below; E ~ 6 N on a triangle mesh) and the
+// edge kernels only gather-add their rows.  The same split is used backwards: with G0 = d loss / d pre0,
+//     d v  += segsum_senders(G0) Ws + segsum_receivers(G0) Wr          (node-level dgrad, proj kernel with B MN-major)
+//     dWs  = segsum_senders(G0)^T v,  dWr = segsum_receivers(G0)^T v   (node-level wgrad)
+// so the edge backward kernel needs only We, W1, W2 and writes only d e and G0.
+//
+// Edge backward kernel (persistent, one CTA per SM, one 128-edge tile at a time):
+//   warps 0-7   epilogue: row = TMEM lane, warp w handles lane quadrant w%4 and column half w/4; bias/ReLU/LayerNorm
+//               forward+backward arithmetic in fp32; every intermediate tile (H1, H2, dY, dH2', dH1') is written as bf16
+//               into one of four rotating 32 KiB shared-memory buffers in the 128B-swizzled operand layout
+//   warps 8-9   producers: cp.async of the next tile's edge rows into the buffer that becomes free after step 4, and the
+//               bias-gradient column sums of the dY / dH2' / dH1' tiles read back from shared memory
+//   warp 10     MMA issuer: per tile 6 chain GEMMs (recompute L0 L1 L2, dgrad dH2 dH1 dXe; A operand K-major from the
+//               buffers, B = resident We/W1/W2 panels, read MN-major for the dgrads) and 3 weight-gradient GEMMs
+//               (dW2 += dY^T H2, dW1 += dH2'^T H1, dWe += dH1'^T e; both operands MN-major from the SAME buffers) whose
+//               fp32 accumulators stay in TMEM for the CTA's whole lifetime.
+// TMEM (512 columns): chain accumulator [0,128) | dW2 [128,256) | dW1 [256,384) | dWe [384,512).
+// Nothing but d e and G0 (and per-CTA fp32 partials at the end) is written to HBM; the previous design wrote six
+// [E,128] workspaces per layer.  All reductions have a fixed order (per-CTA partials, then a sequential sum over CTAs).
+#include "tile_common.cuh"
+
+namespace hgn {
+
+__device__ __forceinline__ void st_shared128(uint32_t addr, const uint32_t* w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Column sums over the 32 lanes of a warp: x[j] is this lane's (= this row's) value in column j.  Returns, in lane j,
+// the sum over all 32 lanes of column j (recursive halving: 31 shuffles).  Fixed association order.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+// =========================================================================================================
+// node projection and its data gradient:  out_o[rows,128] = sum_c in_c[rows,128] * B(chunk chunk0 + o + c)
+//   forward (b_mn = 0): n_in = 1, n_out = 2:  Ps = v Ws^T, Pr = v Wr^T          (B K-major:  out[n] = sum_k in[k] W[n][k])
+//   dgrad   (b_mn = 1): n_in = 2, n_out = 1:  dv = Gs Ws + Gr Wr                (B MN-major: out[k] = sum_n in[n] W[n][k])
+// HBM-bound (256 B read + 512 B written per node row forward).  2-stage cp.async ring, double-buffered TMEM accumulators.
+// =========================================================================================================
+constexpr int kLinEpi = 128, kLinProd = 64;
+constexpr int kLinThreads = kLinEpi + kLinProd + 32;
+
+struct LinArgs {
+  const __nv_bfloat16* in[2];
+  __nv_bfloat16* out[2];
+  int n_in, n_out, b_mn, w0_chunks, chunk0;
+};
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+proj_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, LinArgs la) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t stage_bytes = uint32_t(la.n_in) * kChunkBytes;
+  const uint32_t w_off = 0, st_off = 2 * kChunkBytes, bars_off = st_off + 2 * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bars_off);   // full[2] empty[2] accf[2] acce[2] tmem
+  const PackedTc P(la.w0_chunks);
+  {
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + la.chunk0 * kD;
+    for (int c = 0; c < 2; ++c) load_weight_block(sbase + w_off + c * kChunkBytes, w0g + c * kD, int64_t(la.w0_chunks) * kD, tid, kLinThreads);
+    cp_async_commit();
+    if (tid == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars[0 + s], kLinProd); mbar_init(&bars[2 + s], 1); mbar_init(&bars[4 + s], 1); mbar_init(&bars[6 + s], kLinEpi);
+      }
+      mbar_init_fence();
+    }
+    if (warp == 6) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[8]));
+    cp_async_wait<0>();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars[8]);
+  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp >= 4 && warp < 6) {
+    // ---- producers -----------------------------------------------------------------------------------
+    const int ptid = tid - kLinEpi;
+    if (ptid < 2) mbar_arrive(&bars[2 + ptid]);          // ring starts empty
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int stage = int(it & 1);
+      mbar_wait(&bars[2 + stage], uint32_t(it >> 1) & 1, 40);
+      const int64_t row0 = (blockIdx.x + it * gridDim.x) * kTile;
+      for (int c = 0; c < la.n_in; ++c) {
+        const uint32_t dst = sbase + st_off + stage * stage_bytes + c * kChunkBytes;
+        const __nv_bfloat16* src = la.in[c];
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const int qd = ptid + kLinProd * j, row = qd >> 4, c16 = qd & 15;
+          const int64_t grow = row0 + row;
+          const bool valid = grow < rows;
+          cp_async16_zfill(dst + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), src + (valid ? grow : 0) * kD + c16 * 8, valid);
+        }
+      }
+      cp_async_commit();
+      if (it > 0) {                                       // keep two tiles of loads in flight
+        cp_async_wait<1>();
+        fence_async_smem();
+        mbar_arrive(&bars[0 + int((it - 1) & 1)]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_async_smem();
+    if (my_tiles > 0) mbar_arrive(&bars[0 + int((my_tiles - 1) & 1)]);
+  } else if (warp == 6) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 128, 0, la.b_mn);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = int(it & 1);
+        mbar_wait(&bars[0 + s], uint32_t(it >> 1) & 1, 41);
+        if (it >= 2) mbar_wait(&bars[6 + s], uint32_t((it >> 1) - 1) & 1, 42);     // accumulator set s drained
+        fence_after_sync();
+        for (int o = 0; o < la.n_out; ++o) {
+          const uint32_t acc = tmem_base + s * 256 + o * 128;
+          for (int c = 0; c < la.n_in; ++c) {
+            const uint32_t a_addr = sbase + st_off + s * stage_bytes + c * kChunkBytes;
+            const uint32_t b_addr = sbase + w_off + (o + c) * kChunkBytes;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = sdesc_kmajor(a_addr + (ks >> 2) * kPanel + (ks & 3) * 32);
+              const uint64_t bd = la.b_mn ? sdesc_mnmajor(b_addr + ks * 2048, kPanel) : sdesc_kmajor(b_addr + (ks >> 2) * kPanel + (ks & 3) * 32);
+              mma_ss(acc, ad, bd, idesc, (c | ks) != 0);
+            }
+          }
+        }
+        mma_commit(&bars[2 + s]);
+        mma_commit(&bars[4 + s]);
+      }
+    }
+  } else if (warp < 4) {
+    // ---- epilogue: accumulator -> bf16 rows ----------------------------------------------------------
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const int r = warp * 32 + lane;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int s = int(it & 1);
+      mbar_wait(&bars[4 + s], uint32_t(it >> 1) & 1, 43);
+      fence_after_sync();
+      const int64_t grow = (blockIdx.x + it * gridDim.x) * kTile + r;
+      const bool valid = grow < rows;
+      for (int o = 0; o < la.n_out; ++o) {
+        __nv_bfloat16* op = la.out[o] + (valid ? grow : 0) * kD;
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32], w[16];
+          tmem_ld32(tmem_base + lane_addr + s * 256 + o * 128 + cg * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          if (valid) { stg256(op + cg * 32, w); stg256(op + cg * 32 + 16, w + 8); }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(&bars[6 + s]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc<512>(tmem_base);
+}
+
+// =========================================================================================================
+// edge backward
+// =========================================================================================================
+constexpr int kEbEpiThreads = 256, kEbProdThreads = 64;
+constexpr int kEbThreads = kEbEpiThreads + kEbProdThreads + 32;    // 11 warps
+constexpr uint32_t kEbWe = 0, kEbW1 = kChunkBytes, kEbW2 = 2 * kChunkBytes, kEbBuf = 3 * kChunkBytes;
+constexpr uint32_t kEbParams = kEbBuf + 4 * kChunkBytes;           // b0 b1 b2 gamma beta (fp32 x 128 each)
+constexpr uint32_t kEbBars = kEbParams + 5 * kD * 4;
+constexpr uint32_t kEbSmem = kEbBars + 128;                        // 232 064 B of the 232 448 available
+// kEbG + k / kEbCs + k (k = 0 dY, 1 dH2', 2 dH1'): one barrier per tile-in-buffer hand-over, so each completes exactly one
+// phase per tile and no waiter can fall two phases behind (a parity wait cannot tell phase n from phase n + 2)
+enum { kEbFull = 0, kEbFree = 1, kEbAcc = 2, kEbEpi = 3, kEbG = 4, kEbCs = 7, kEbTmem = 10 };
+
+struct EdgeBwdArgs {
+  const __nv_bfloat16 *edge, *proj_s, *proj_r;
+  const int32_t *senders, *receivers;
+  const __nv_bfloat16* grad_out;    // [E,128] dense part of d loss / d e' (may be null)
+  const __nv_bfloat16* grad_agg;    // [N,128] gathered through receivers: gradient of the 'sum' aggregate (may be null)
+  __nv_bfloat16 *grad_edge, *grad_pre0;
+  float* w_partial;                 // [grid][3][128][128]  z = 0: dWe, 1: dW1, 2: dW2
+  float* epi_colpart;               // [grid][4][2][128]    beta, gamma partial column sums per lane quadrant
+  float* prod_colpart;              // [grid][3][128]       db2, db1, db0
+};
+
+__global__ void __launch_bounds__(kEbThreads, 1)
+edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, EdgeBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEbBars);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PackedTc P(3);
+  float* prm = reinterpret_cast<float*>(smem + kEbParams);
+  {
+    const float* pg = reinterpret_cast<const float*>(packed + P.params);
+    for (int i = tid; i < 5 * kD; i += kEbThreads) prm[i] = pg[i];
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    load_weight_block(sbase + kEbWe, w0g + 2 * kD, 3 * kD, tid, kEbThreads);
+    load_weight_block(sbase + kEbW1, reinterpret_cast<const __nv_bfloat16*>(packed + P.w1), kD, tid, kEbThreads);
+    load_weight_block(sbase + kEbW2, reinterpret_cast<const __nv_bfloat16*>(packed + P.w2), kD, tid, kEbThreads);
+    cp_async_commit();
+    if (tid == 0) {
+      mbar_init(&bars[kEbFull], kEbProdThreads);
+      mbar_init(&bars[kEbFree], 1);
+      mbar_init(&bars[kEbAcc], 1);
+      mbar_init(&bars[kEbEpi], kEbEpiThreads);
+      for (int k = 0; k < 3; ++k) { mbar_init(&bars[kEbG + k], kEbEpiThreads); mbar_init(&bars[kEbCs + k], kEbProdThreads); }
+      mbar_init_fence();
+    }
+    if (warp == 10) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[kEbTmem]));
+    cp_async_wait<0>();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars[kEbTmem]);
+  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // buffer roles of tile t: 0 = S (edge rows), 1 = A (H1), 2 = B (H2, then dH2'), 3 = C (dY, then dH1'); they rotate by one
+  // buffer per tile so that S(t+1) = A(t), the first buffer that falls free (after step 4), receives the prefetch
+  auto buf = [&](int role, int64_t t) -> uint32_t { return sbase + kEbBuf + uint32_t((role + t) & 3) * kChunkBytes; };
+
+  if (warp == 8 || warp == 9) {
+    // =============================== producers =========================================================
+    const int ptid = tid - kEbEpiThreads, pw = warp - 8;
+    auto load_e = [&](int64_t t) {
+      const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTile;
+      const uint32_t dst = buf(0, t);
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int qd = ptid + kEbProdThreads * j, row = qd >> 4, c16 = qd & 15;
+        const int64_t grow = row0 + row;
+        const bool valid = grow < rows;
+        cp_async16_zfill(dst + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), a.edge + (valid ? grow : 0) * kD + c16 * 8, valid);
+      }
+      cp_async_commit();
+    };
+    // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..), lane l the column pair 2l, 2l+1
+    auto colsum = [&](uint32_t base, float& s0, float& s1) {
+      const uint32_t pbase = base + pw * kPanel + (lane & 3) * 4;
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll 16
+      for (int row = 0; row < kTile; ++row) {
+        const uint32_t w = ld_shared32(pbase + (row >> 3) * 1024 + (row & 7) * 128 + ((((lane >> 2) ^ (row & 7)) & 7) << 4));
+        t0 += bf16_lo(w);
+        t1 += bf16_hi(w);
+      }
+      s0 += t0;
+      s1 += t1;
+    };
+    float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    if (my_tiles > 0) {
+      load_e(0);
+      cp_async_wait<0>();
+      fence_async_smem();
+      mbar_arrive(&bars[kEbFull]);
+    }
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const uint32_t par = uint32_t(t) & 1;
+      mbar_wait(&bars[kEbG + 0], par, 50);
+      colsum(buf(3, t), cs[0][0], cs[0][1]);                 // dY
+      mbar_arrive(&bars[kEbCs + 0]);
+      mbar_wait(&bars[kEbG + 1], par, 51);
+      colsum(buf(2, t), cs[1][0], cs[1][1]);                 // dH2'
+      mbar_arrive(&bars[kEbCs + 1]);
+      const bool more = t + 1 < my_tiles;
+      if (more) {
+        mbar_wait(&bars[kEbFree], par, 52);
+        load_e(t + 1);
+      }
+      mbar_wait(&bars[kEbG + 2], par, 53);
+      colsum(buf(3, t), cs[2][0], cs[2][1]);                 // dH1'
+      mbar_arrive(&bars[kEbCs + 2]);
+      if (more) {
+        cp_async_wait<0>();
+        fence_async_smem();
+        mbar_arrive(&bars[kEbFull]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float2 v = make_float2(cs[k][0], cs[k][1]);
+      *reinterpret_cast<float2*>(a.prod_colpart + (int64_t(blockIdx.x) * 3 + k) * kD + pw * 64 + lane * 2) = v;
+    }
+  } else if (warp == 10) {
+    // =============================== MMA issuer =========================================================
+    if (lane == 0) {
+      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0), id_kmn = make_idesc_bf16(128, 128, 0, 1), id_mm = make_idesc_bf16(128, 128, 1, 1);
+      const uint32_t acc = tmem_base, dW2 = tmem_base + 128, dW1 = tmem_base + 256, dWe = tmem_base + 384;
+      uint32_t epi_phase = 0;
+      auto wait_epi = [&]() {
+        mbar_wait(&bars[kEbEpi], epi_phase++ & 1, 60);
+        fence_after_sync();
+      };
+      auto chain = [&](uint32_t a_addr, uint32_t b_addr, bool b_mn) {      // acc = A[128 x 128] (K-major) * B
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = sdesc_kmajor(a_addr + (ks >> 2) * kPanel + (ks & 3) * 32);
+          const uint64_t bd = b_mn ? sdesc_mnmajor(b_addr + ks * 2048, kPanel) : sdesc_kmajor(b_addr + (ks >> 2) * kPanel + (ks & 3) * 32);
+          mma_ss(acc, ad, bd, b_mn ? id_kmn : id_kk, ks != 0);
+        }
+      };
+      auto wgrad = [&](uint32_t d, uint32_t g_addr, uint32_t z_addr, bool first) {   // d (+)= G^T Z over the tile's 128 rows
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          mma_ss(d, sdesc_mnmajor(g_addr + ks * 2048, kPanel), sdesc_mnmajor(z_addr + ks * 2048, kPanel), id_mm, !(first && ks == 0));
+      };
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const uint32_t S = buf(0, t), A = buf(1, t), B = buf(2, t), C = buf(3, t);
+        const bool first = t == 0;
+        mbar_wait(&bars[kEbFull], uint32_t(t) & 1, 61);
+        fence_after_sync();
+        if (!first) wait_epi();                                  // previous tile's last epilogue has drained the accumulator
+        chain(S, sbase + kEbWe, false);  mma_commit(&bars[kEbAcc]);                                    // 0: e We^T
+        wait_epi(); chain(A, sbase + kEbW1, false);  mma_commit(&bars[kEbAcc]);                        // 1: H1 W1^T
+        wait_epi(); chain(B, sbase + kEbW2, false);  mma_commit(&bars[kEbAcc]);                        // 2: H2 W2^T
+        wait_epi(); chain(C, sbase + kEbW2, true);   wgrad(dW2, C, B, first); mma_commit(&bars[kEbAcc]);   // 3: dY W2 ; dW2
+        wait_epi(); chain(B, sbase + kEbW1, true);   wgrad(dW1, B, A, first); mma_commit(&bars[kEbAcc]);   // 4: dH2' W1 ; dW1
+        mma_commit(&bars[kEbFree]);
+        wait_epi(); chain(C, sbase + kEbWe, true);   wgrad(dWe, C, S, first); mma_commit(&bars[kEbAcc]);   // 5: dH1' We ; dWe
+      }
+    }
+  } else {
+    // =============================== epilogue ============================================================
+    const int q = warp & 3, hh = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t acc = tmem_base + lane_addr + hh * 64;
+    const float *b0 = prm + hh * 64, *b1 = prm + kD + hh * 64, *b2 = prm + 2 * kD + hh * 64, *gam = prm + 3 * kD + hh * 64;
+    uint32_t acc_phase = 0;
+    float cbeta[2] = {0.f, 0.f}, cgamma[2] = {0.f, 0.f};
+    auto wait_acc = [&](int tag) {
+      mbar_wait(&bars[kEbAcc], acc_phase++ & 1, tag);
+      fence_after_sync();
+    };
+    // k-th column-sum hand-over of (local) tile tt: the producers have finished reading that tile from its buffer
+    auto wait_cs = [&](int k, int64_t tt) { mbar_wait(&bars[kEbCs + k], uint32_t(tt) & 1, 70 + k); };
+    auto done = [&](int producers_k) {   // producers_k >= 0: the tile just written is also the producers' column-sum input k
+      fence_async_smem();          // generic-proxy tile writes -> visible to the tensor core's async-proxy reads
+      fence_before_sync();
+      mbar_arrive(&bars[kEbEpi]);
+      if (producers_k >= 0) mbar_arrive(&bars[kEbG + producers_k]);
+    };
+    auto store_cg = [&](uint32_t bufaddr, int cg, const uint32_t* w) {      // 32 columns (16 packed words) of row r
+      const uint32_t rowbase = bufaddr + hh * kPanel;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_shared128(rowbase + sw128_chunk(r, cg * 4 + k), w + 4 * k);
+    };
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const uint32_t A = buf(1, t), B = buf(2, t), C = buf(3, t);
+      // row-half exchange area (LayerNorm statistics): the first 4 KiB of buffer C, which is idle until dY is written into it
+      float2* xch = reinterpret_cast<float2*>(smem + (C - sbase));
+      const int64_t grow = (blockIdx.x + t * gridDim.x) * kTile + r;
+      const bool valid = grow < rows;
+      const int64_t si = valid ? __ldg(a.senders + grow) : 0, ri = valid ? __ldg(a.receivers + grow) : 0;
+      uint32_t mask1[2], mask2[2];
+      // ---- E0: H1 = relu(e We^T + Ps[s] + Pr[r] + b0) -> A ---------------------------------------------------
+      {
+        const __nv_bfloat16* psrow = a.proj_s + si * kD + hh * 64;
+        const __nv_bfloat16* prrow = a.proj_r + ri * kD + hh * 64;
+        uint32_t pq[32], pn[32];
+        ldg256(psrow, pq); ldg256(psrow + 16, pq + 8); ldg256(prrow, pq + 16); ldg256(prrow + 16, pq + 24);
+        if (t > 0) wait_cs(1, t - 1);                           // the producers' dH2' column sum has left this buffer
+        wait_acc(100);
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          if (cg == 0) { ldg256(psrow + 32, pn); ldg256(psrow + 48, pn + 8); ldg256(prrow + 32, pn + 16); ldg256(prrow + 48, pn + 24); }
+          tmem_ld_wait();
+          const uint32_t* pp = cg == 0 ? pq : pn;
+          uint32_t h[16], m = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cg * 32 + 2 * j;
+            const float x0 = fmaxf(__uint_as_float(v[2 * j]) + bf16_lo(pp[j]) + bf16_lo(pp[16 + j]) + b0[col], 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bf16_hi(pp[j]) + bf16_hi(pp[16 + j]) + b0[col + 1], 0.f);
+            h[j] = pack_bf16(x0, x1);
+            m |= (x0 > 0.f ? (1u << (2 * j)) : 0u) | (x1 > 0.f ? (1u << (2 * j + 1)) : 0u);
+          }
+          mask1[cg] = m;
+          store_cg(A, cg, h);
+        }
+        done(-1);
+      }
+      // ---- E1: H2 = relu(H1 W1^T + b1) -> B -----------------------------------------------------------------------
+      {
+        if (t > 0) wait_cs(2, t - 1);                           // previous tile's dH1' column sum has left this buffer
+        wait_acc(101);
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          uint32_t h[16], m = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cg * 32 + 2 * j;
+            const float x0 = fmaxf(__uint_as_float(v[2 * j]) + b1[col], 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + b1[col + 1], 0.f);
+            h[j] = pack_bf16(x0, x1);
+            m |= (x0 > 0.f ? (1u << (2 * j)) : 0u) | (x1 > 0.f ? (1u << (2 * j + 1)) : 0u);
+          }
+          mask2[cg] = m;
+          store_cg(B, cg, h);
+        }
+        done(-1);
+      }
+      // ---- E2: y = H2 W2^T + b2 ; LayerNorm forward statistics and backward -> dY -> C --------------------------------
+      uint32_t dreg[32];                                        // dO = grad_out[row] + grad_agg[receiver] of my 64 columns, bf16
+      {
+        const __nv_bfloat16* dorow = a.grad_out + grow * kD + hh * 64;
+        const __nv_bfloat16* garow = a.grad_agg + ri * kD + hh * 64;
+        const bool has_do = valid && a.grad_out != nullptr, has_ga = valid && a.grad_agg != nullptr;
+        uint32_t dq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dq[j] = 0u;
+        if (has_do) { ldg256(dorow, dq); ldg256(dorow + 16, dq + 8); }
+        if (has_ga) { ldg256(garow, dq + 16); ldg256(garow + 16, dq + 24); }
+        wait_acc(102);
+        // statistics of my 64 columns, merged with the other half of the row (Chan's parallel update, equal counts)
+        float s = 0.f;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + b2[cg * 32 + j];
+        }
+        const float mean_h = s * (1.0f / 64.0f);
+        float m2h = 0.f;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(v[j]) + b2[cg * 32 + j] - mean_h; m2h = fmaf(d, d, m2h); }
+        }
+        xch[hh * kTile + r] = make_float2(mean_h, m2h);
+        epi_bar_sync();
+        const float2 oth = xch[(1 - hh) * kTile + r];
+        const float mean = 0.5f * (mean_h + oth.x);
+        const float dm = mean_h - oth.x;
+        const float rstd = rsqrtf((m2h + oth.y + 32.0f * dm * dm) * (1.0f / kD) + kEps);
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          // dO of this column group, rounded to bf16 once (the value every later use sees); then the loads of the next group
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            dreg[cg * 16 + j] = pack_bf16(bf16_lo(dq[j]) + bf16_lo(dq[16 + j]), bf16_hi(dq[j]) + bf16_hi(dq[16 + j]));
+          if (cg == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dq[j] = 0u;
+            if (has_do) { ldg256(dorow + 32, dq); ldg256(dorow + 48, dq + 8); }
+            if (has_ga) { ldg256(garow + 32, dq + 16); ldg256(garow + 48, dq + 24); }
+          }
+          tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dj = (j & 1) ? bf16_hi(dreg[cg * 16 + (j >> 1)]) : bf16_lo(dreg[cg * 16 + (j >> 1)]);
+            const float yh = (__uint_as_float(v[j]) + b2[cg * 32 + j] - mean) * rstd;
+            const float z = dj * gam[cg * 32 + j];
+            m1 += z;
+            m2 = fmaf(z, yh, m2);
+            p[j] = dj * yh;
+          }
+          cgamma[cg] += warp_colsum32(p, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) p[j] = (j & 1) ? bf16_hi(dreg[cg * 16 + (j >> 1)]) : bf16_lo(dreg[cg * 16 + (j >> 1)]);
+          cbeta[cg] += warp_colsum32(p, lane);
+        }
+        xch[2 * kTile + hh * kTile + r] = make_float2(m1, m2);
+        epi_bar_sync();
+        const float2 o2 = xch[2 * kTile + (1 - hh) * kTile + r];
+        m1 = (m1 + o2.x) * (1.0f / kD);
+        m2 = (m2 + o2.y) * (1.0f / kD);
+        epi_bar_sync();                                         // every thread has read both exchanges: dY may overwrite them
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cg * 32 + 2 * j;
+            const float yh0 = (__uint_as_float(v[2 * j]) + b2[col] - mean) * rstd;
+            const float yh1 = (__uint_as_float(v[2 * j + 1]) + b2[col + 1] - mean) * rstd;
+            const float dy0 = rstd * (bf16_lo(dreg[cg * 16 + j]) * gam[col] - m1 - yh0 * m2);
+            const float dy1 = rstd * (bf16_hi(dreg[cg * 16 + j]) * gam[col + 1] - m1 - yh1 * m2);
+            o[j] = pack_bf16(dy0, dy1);
+          }
+          store_cg(C, cg, o);
+        }
+        done(0);
+      }
+      // ---- E3: dH2' = (dY W2) * [H2 > 0] -> B ---------------------------------------------------------------------
+      {
+        wait_acc(103);
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          const uint32_t m = mask2[cg];
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            o[j] = pack_bf16((m >> (2 * j)) & 1u ? __uint_as_float(v[2 * j]) : 0.f, (m >> (2 * j + 1)) & 1u ? __uint_as_float(v[2 * j + 1]) : 0.f);
+          store_cg(B, cg, o);
+        }
+        done(1);
+      }
+      // ---- E4: G0 = dH1' = (dH2' W1) * [H1 > 0] -> C and -> HBM -----------------------------------------------------------
+      {
+        wait_cs(0, t);                                          // the producers' dY column sum has left buffer C
+        wait_acc(104);
+        __nv_bfloat16* g0row = a.grad_pre0 + (valid ? grow : 0) * kD + hh * 64;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          const uint32_t m = mask1[cg];
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            o[j] = pack_bf16((m >> (2 * j)) & 1u ? __uint_as_float(v[2 * j]) : 0.f, (m >> (2 * j + 1)) & 1u ? __uint_as_float(v[2 * j + 1]) : 0.f);
+          store_cg(C, cg, o);
+          if (valid) { stg256(g0row + cg * 32, o); stg256(g0row + cg * 32 + 16, o + 8); }
+        }
+        done(2);
+      }
+      // ---- E5: d e = dH1' We + dO -> HBM -------------------------------------------------------------------------------
+      {
+        wait_acc(105);
+        __nv_bfloat16* derow = a.grad_edge + (valid ? grow : 0) * kD + hh * 64;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(acc + cg * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            o[j] = pack_bf16(__uint_as_float(v[2 * j]) + bf16_lo(dreg[cg * 16 + j]), __uint_as_float(v[2 * j + 1]) + bf16_hi(dreg[cg * 16 + j]));
+          if (valid) { stg256(derow + cg * 32, o); stg256(derow + cg * 32 + 16, o + 8); }
+        }
+        done(-1);
+      }
+    }
+    // ---- drain the weight-gradient accumulators and the LayerNorm vector partials ---------------------------------------
+    // (the last wait_acc above saw the commit that followed every MMA of this CTA)
+#pragma unroll 1
+    for (int z = 0; z < 3; ++z) {
+      const uint32_t col0 = 384u - 128u * uint32_t(z);           // z = 0: dWe, 1: dW1, 2: dW2
+      float* dst = a.w_partial + ((int64_t(blockIdx.x) * 3 + z) * kD + r) * kD + hh * 64;
+#pragma unroll 1
+      for (int cg = 0; cg < 2; ++cg) {
+        uint32_t v[32];
+        if (my_tiles > 0) {
+          tmem_ld32(tmem_base + lane_addr + col0 + hh * 64 + cg * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(dst + cg * 32 + 4 * k) = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                                                          __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
+      }
+    }
+#pragma unroll
+    for (int cg = 0; cg < 2; ++cg) {
+      float* cp = a.epi_colpart + ((int64_t(blockIdx.x) * 4 + q) * 2) * kD + hh * 64 + cg * 32 + lane;
+      cp[0] = cbeta[cg];
+      cp[kD] = cgamma[cg];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc<512>(tmem_base);
+}
+
+// fixed-order reduction of the per-CTA partials of edge_bwd_tc_kernel
+__global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, const float* __restrict__ epi_colpart,
+                                       const float* __restrict__ prod_colpart, int parts, float* __restrict__ gW0, float* __restrict__ gW1,
+                                       float* __restrict__ gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * kD * kD) {
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) s += w_partial[int64_t(p) * 3 * kD * kD + i];
+    const int z = i / (kD * kD), o = (i / kD) % kD, c = i % kD;
+    if (z == 0) gW0[int64_t(o) * 3 * kD + 2 * kD + c] = s;
+    else if (z == 1) gW1[o * kD + c] = s;
+    else gW2[o * kD + c] = s;
+  } else if (i < 3 * kD * kD + 5 * kD) {
+    const int k = (i - 3 * kD * kD) / kD, c = i % kD;
+    float s = 0.f;
+    if (k < 3) {
+      for (int p = 0; p < parts; ++p) s += prod_colpart[(int64_t(p) * 3 + k) * kD + c];
+      (k == 0 ? gb2 : k == 1 ? gb1 : gb0)[c] = s;
+    } else {
+      for (int p = 0; p < parts * 4; ++p) s += epi_colpart[(int64_t(p) * 2 + (k - 3)) * kD + c];
+      (k == 3 ? gbeta : ggamma)[c] = s;
+    }
+  }
+}
+
+// gW0[:, col0 : col0+128] = sum_p partial[p][z]   (partials of the pair weight-gradient kernel, [parts][n_z][128][128])
+__global__ void reduce_w0_block_kernel(const float* __restrict__ partial, int parts, int n_z, int z, float* __restrict__ gW0, int ld, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kD * kD) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partial[(int64_t(p) * n_z + z) * kD * kD + i];
+  gW0[int64_t(i / kD) * ld + col0 + (i % kD)] = s;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+int tc_pair_wgrad(int64_t rows, const void* Ga, const void* Za, const void* Gb, const void* Zb, float* partial, int parts,
+                  cudaStream_t st);                              // mlp_tc.cu
+int tc_pair_wgrad_parts(int64_t rows);
+
+static int configure_edge_kernels() {
+  static bool configured = false;
+  if (!configured) {
+    uint32_t* dbg = debug_buffer_device();
+    HGN_CUDA_OK(cudaMemcpyToSymbol(tc05::g_debug_words, &dbg, sizeof(dbg)));
+    HGN_CUDA_OK(cudaFuncSetAttribute(edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kEbSmem)));
+    HGN_CUDA_OK(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kChunkBytes + 4 * kChunkBytes + 128));
+    configured = true;
+  }
+  return HGN_OK;
+}
+
+static int launch_proj(int64_t rows, const void* packed, const LinArgs& la, const char* name, cudaStream_t st) {
+  if (int rc = configure_edge_kernels()) return rc;
+  const int64_t tiles = ceil_div(rows, kTile);
+  const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
+  const size_t smem = size_t(2 + 2 * la.n_in) * kChunkBytes + 128;
+  HGN_TIMED(name, st);
+  proj_tc_kernel<<<grid, kLinThreads, smem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), la);
+  HGN_LAUNCH_OK(name);
+  return HGN_OK;
+}
+
+int edge_project_forward_tc(int64_t num_nodes, const void* v, const void* packed, void* proj_s, void* proj_r, cudaStream_t st) {
+  LinArgs la{};
+  la.in[0] = static_cast<const __nv_bfloat16*>(v);
+  la.out[0] = static_cast<__nv_bfloat16*>(proj_s);
+  la.out[1] = static_cast<__nv_bfloat16*>(proj_r);
+  la.n_in = 1; la.n_out = 2; la.b_mn = 0; la.w0_chunks = 3; la.chunk0 = 0;
+  return launch_proj(num_nodes, packed, la, "edge_project_fwd", st);
+}
+
+size_t edge_project_backward_workspace_tc(int64_t num_nodes) {
+  return size_t(tc_pair_wgrad_parts(num_nodes)) * 2 * kD * kD * sizeof(float) + 256;
+}
+
+int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
+                             float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (workspace_bytes < edge_project_backward_workspace_tc(num_nodes)) { set_error("edge_project_backward: workspace too small"); return HGN_ERR_WORKSPACE; }
+  LinArgs la{};
+  la.in[0] = static_cast<const __nv_bfloat16*>(grad_s);
+  la.in[1] = static_cast<const __nv_bfloat16*>(grad_r);
+  la.out[0] = static_cast<__nv_bfloat16*>(grad_v);
+  la.n_in = 2; la.n_out = 1; la.b_mn = 1; la.w0_chunks = 3; la.chunk0 = 0;
+  if (int rc = launch_proj(num_nodes, packed, la, "edge_project_dgrad", st)) return rc;
+  float* partial = static_cast<float*>(workspace);
+  const int parts = tc_pair_wgrad_parts(num_nodes);
+  if (int rc = tc_pair_wgrad(num_nodes, grad_s, v, grad_r, v, partial, parts, st)) return rc;
+  {
+    HGN_TIMED("reduce_weight_partials", st);
+    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, parts, 2, 1, grad_W0, 3 * kD, 0);        // Gs^T v -> columns 0:128
+    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, parts, 2, 0, grad_W0, 3 * kD, kD);       // Gr^T v -> columns 128:256
+  }
+  HGN_LAUNCH_OK("edge_project_backward reductions");
+  return HGN_OK;
+}
+
+int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
+                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st) {
+  hgn_chunks ch{};
+  ch.n_chunks = 1;
+  ch.src[0] = edge;
+  PreAdd pre{};
+  pre.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
+  pre.proj_r = static_cast<const __nv_bfloat16*>(proj_r);
+  pre.senders = senders;
+  pre.receivers = receivers;
+  pre.w0_chunks = 3;
+  pre.w0_chunk0 = 2;
+  return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc", st);
+}
+
+struct EdgeBwdLayout { size_t w_partial, epi, prod, total; int grid; };
+static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
+  EdgeBwdLayout L{};
+  const int64_t tiles = ceil_div(rows > 0 ? rows : 1, kTile);
+  L.grid = int(tiles < tc_sm_count() ? tiles : tc_sm_count());
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.w_partial = take(size_t(L.grid) * 3 * kD * kD * 4);
+  L.epi = take(size_t(L.grid) * 4 * 2 * kD * 4);
+  L.prod = take(size_t(L.grid) * 3 * kD * 4);
+  L.total = off;
+  return L;
+}
+
+size_t edge_update_backward_workspace_tc(int64_t num_edges) { return edge_bwd_layout(num_edges).total; }
+
+int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
+                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
+                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
+                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const EdgeBwdLayout L = edge_bwd_layout(num_edges);
+  if (workspace_bytes < L.total) { set_error("edge_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  if (int rc = configure_edge_kernels()) return rc;
+  char* ws = static_cast<char*>(workspace);
+  EdgeBwdArgs a{};
+  a.edge = static_cast<const __nv_bfloat16*>(edge);
+  a.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
+  a.proj_r = static_cast<const __nv_bfloat16*>(proj_r);
+  a.senders = senders;
+  a.receivers = receivers;
+  a.grad_out = static_cast<const __nv_bfloat16*>(grad_out);
+  a.grad_agg = static_cast<const __nv_bfloat16*>(grad_agg);
+  a.grad_edge = static_cast<__nv_bfloat16*>(grad_edge);
+  a.grad_pre0 = static_cast<__nv_bfloat16*>(grad_pre0);
+  a.w_partial = reinterpret_cast<float*>(ws + L.w_partial);
+  a.epi_colpart = reinterpret_cast<float*>(ws + L.epi);
+  a.prod_colpart = reinterpret_cast<float*>(ws + L.prod);
+  const int64_t tiles = ceil_div(num_edges, kTile);
+  {
+    HGN_TIMED("edge_bwd_tc", st);
+    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(num_edges, tiles, static_cast<const uint8_t*>(packed), a);
+  }
+  HGN_LAUNCH_OK("edge_bwd_tc");
+  {
+    HGN_TIMED("reduce_weight_partials", st);
+    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, gW0, gW1, gW2,
+                                                                              gb0, gb1, gb2, ggamma, gbeta);
+  }
+  HGN_LAUNCH_OK("edge_bwd_reduce");
+  return HGN_OK;
+}
+
+}  // namespace hgn

@@ -23,37 +23,9 @@
 // TMEM over a CTA's whole row range; per-CTA partials are reduced in a fixed order afterwards.
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "tc05.cuh"
+#include "tile_common.cuh"
 
 namespace hgn {
-
-using namespace tc05;
-
-constexpr int kTile = 128;                     // rows per tile = TMEM lanes
-constexpr int kPanel = kPanelBytes128;         // 16 KiB: [128][64] bf16
-constexpr int kChunkBytes = 2 * kPanel;        // one 128x128 bf16 operand: 32 KiB
-constexpr int kStages = 2;
-constexpr int kEpiThreads = 256;               // warps 0-7
-constexpr int kProdThreads = 128;              // warps 8-11
-constexpr int kTileThreads = kEpiThreads + kProdThreads + 32;
-constexpr int kMaxResidentChunks = 3;
-constexpr float kEps = 1e-5f;
-
-// fixed-order reductions of the per-CTA weight-gradient partials (defined in mlp_f32.cu)
-void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks, float* gW0, float* gW1, float* gW2, cudaStream_t st);
-
-struct PackedTc {   // byte offsets inside the packed blob
-  size_t w0, w1, w2, params, total;   // params: b0 b1 b2 gamma beta (fp32 x 128 each)
-  __host__ __device__ explicit PackedTc(int n_chunks) {
-    size_t o = 0;
-    w0 = o; o += size_t(n_chunks) * kD * kD * 2;
-    w1 = o; o += size_t(kD) * kD * 2;
-    w2 = o; o += size_t(kD) * kD * 2;
-    params = o; o += 5 * kD * 4;
-    total = o;
-  }
-};
 
 __global__ void pack_tc_kernel(int n_chunks, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
                                const float* b2, const float* gamma, const float* beta, uint8_t* packed) {
@@ -98,14 +70,6 @@ enum { kBarFull = 0, kBarEmpty = 2, kBarAcc = 4, kBarEpi = 10, kBarDone = 12, kB
 constexpr int kAccSlots = 3;                    // TMEM accumulators [0,128) [128,256) [256,384)
 constexpr uint32_t kAopCol = 384;               // bf16 A operands of the two epilogue groups: [384,448) [448,512)
 
-// copy a [128][128] bf16 row-major block (row pitch `ld` elements) into two SW128 panels
-__device__ __forceinline__ void load_weight_block(uint32_t smem_dst, const __nv_bfloat16* __restrict__ g, int64_t ld, int tid, int nthreads) {
-  for (int q = tid; q < kTile * 16; q += nthreads) {
-    const int row = q >> 4, c16 = q & 15;
-    cp_async16(smem_dst + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), g + int64_t(row) * ld + c16 * 8);
-  }
-}
-
 struct BwdArgs {
   const __nv_bfloat16* grad_out;
   __nv_bfloat16* grad_chunk[HGN_MAX_CHUNKS];
@@ -136,22 +100,23 @@ template <bool kBwd>
 __global__ void __launch_bounds__(kTileThreads, 1)
 mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch, const uint8_t* __restrict__ packed,
                    int w0_resident, const __nv_bfloat16* __restrict__ resid, int64_t resid_off, __nv_bfloat16* __restrict__ out,
-                   BwdArgs bw) {
+                   BwdArgs bw, PreAdd pre) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nch = ch.n_chunks;
   const TileSmem S(nch, w0_resident != 0, kBwd);
-  const PackedTc P(nch);
+  const int w0_chunks = pre.w0_chunks > 0 ? pre.w0_chunks : nch;
+  const PackedTc P(w0_chunks);
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SW128 atoms need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S.bars);
   float* sparams = reinterpret_cast<float*>(smem + S.params);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t k0 = int64_t(nch) * kD;
+  const int64_t k0 = int64_t(w0_chunks) * kD;
   const int n_steps = kBwd ? 5 + nch : 3;
 
   // ---- prologue: resident weights, parameters, barriers, TMEM ------------------------------------
   {
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
     if (w0_resident)
       for (int c = 0; c < nch; ++c) load_weight_block(sbase + S.w0 + c * kChunkBytes, w0g + c * kD, k0, tid, kTileThreads);
     load_weight_block(sbase + S.w1, reinterpret_cast<const __nv_bfloat16*>(packed + P.w1), kD, tid, kTileThreads);
@@ -184,7 +149,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
     const int gt = ptid & 63;
     if (gt == 0) mbar_arrive(&bars[kBarEmpty + group]);   // the ring starts empty
     const uint32_t stage_addr = sbase + S.stages + group * S.stage_bytes;
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
     const int64_t n_slots = my_tiles * nch;
     const int c16 = gt & 15, rbase = gt >> 4;    // this thread copies 16-byte piece c16 of rows rbase + 4 j
     // all 32 source-row indices of a slot are fetched in one batch, one slot ahead of the copies
@@ -231,7 +196,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
     int wg_step[2] = {0, 0};
     uint32_t wg_sig[2] = {0, 0}, wg_fin[2] = {0, 0};
     uint32_t acc_busy = 0, w0b_uses = 0, idle = 0;
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
     while (done < my_tiles) {
       bool progressed = false;
       // lane 0 polls the barriers once per round and broadcasts, so the whole warp takes the same path
@@ -360,6 +325,15 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
       // ---- hidden layers: bias + ReLU -> bf16 A operand in TMEM -------------------------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
+        const bool add_proj = !kBwd && layer == 0 && pre.proj_s != nullptr;
+        // projected mode: rows of the two per-node tables, fetched (L2) while the layer-0 MMAs run
+        const __nv_bfloat16 *psrow = nullptr, *prrow = nullptr;
+        uint32_t pq[32];
+        if (add_proj) {
+          psrow = pre.proj_s + int64_t(valid ? __ldg(pre.senders + grow) : 0) * kD;
+          prrow = pre.proj_r + int64_t(valid ? __ldg(pre.receivers + grow) : 0) * kD;
+          ldg256(psrow, pq); ldg256(psrow + 16, pq + 8); ldg256(prrow, pq + 16); ldg256(prrow + 16, pq + 24);
+        }
         wait_acc();
         const float* bias = sparams + layer * kD;
         __nv_bfloat16* hws = kBwd ? (layer == 0 ? bw.H1 : bw.H2) + lrow * kD : nullptr;
@@ -368,6 +342,22 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
+          if (add_proj) {
+            uint32_t pn[32];
+            if (cg < 3) {   // next column group's table rows in flight while this one is consumed
+              ldg256(psrow + (cg + 1) * 32, pn); ldg256(psrow + (cg + 1) * 32 + 16, pn + 8);
+              ldg256(prrow + (cg + 1) * 32, pn + 16); ldg256(prrow + (cg + 1) * 32 + 16, pn + 24);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16_lo(pq[j]) + bf16_lo(pq[16 + j]));
+              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16_hi(pq[j]) + bf16_hi(pq[16 + j]));
+            }
+            if (cg < 3) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pq[j] = pn[j];
+            }
+          }
           uint32_t h[16];
           uint32_t m = 0;
 #pragma unroll
@@ -733,7 +723,7 @@ int mlp_tc_pack(int n_chunks, const float* W0, const float* b0, const float* W1,
   return HGN_OK;
 }
 
-static int sm_count() {
+int tc_sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -743,8 +733,6 @@ static int sm_count() {
   }
   return n;
 }
-
-uint32_t* debug_buffer_device();   // cabi.cu: host-mapped words, readable after a device trap
 
 static int configure_kernels() {
   static bool configured = false;
@@ -759,21 +747,51 @@ static int configure_kernels() {
   return HGN_OK;
 }
 
+int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
+                       const PreAdd& pre, const char* name, cudaStream_t st);
+
 int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
                    cudaStream_t st) {
+  return mlp_tc_forward_pre(rows, ch, packed, resid, resid_off, out, PreAdd{}, "mlp_tile_tc_fwd", st);
+}
+
+int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
+                       const PreAdd& pre, const char* name, cudaStream_t st) {
   const int nch = ch->n_chunks;
   const bool resident = nch <= kMaxResidentChunks;
   const TileSmem S(nch, resident, false);
   if (int rc = configure_kernels()) return rc;
   const int64_t tiles = ceil_div(rows, kTile);
-  const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
+  const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
   BwdArgs none{};
   { const char* ab = getenv("HGN_TC_ABLATE"); none.ablate = ab ? atoi(ab) : 0; }
-  HGN_TIMED("mlp_tile_tc_fwd", st);
+  HGN_TIMED(name, st);
   mlp_tile_tc_kernel<false><<<grid, kTileThreads, S.total, st>>>(rows, tiles, 0, *ch, static_cast<const uint8_t*>(packed), resident ? 1 : 0,
                                                                  static_cast<const __nv_bfloat16*>(resid), resid_off,
-                                                                 static_cast<__nv_bfloat16*>(out), none);
+                                                                 static_cast<__nv_bfloat16*>(out), none, pre);
   HGN_LAUNCH_OK("mlp_fwd_tc");
+  return HGN_OK;
+}
+
+// dWa = Ga^T Za and dWb = Gb^T Zb over dense [rows,128] bf16 operands (node-level weight gradients of the projected edge
+// update): per-part fp32 partials [parts][2][128][128], z = 1: a, z = 0: b.
+int tc_pair_wgrad_parts(int64_t rows) {
+  const int64_t r = rows > 0 ? rows : 1;
+  return int(r >= int64_t(tc_sm_count()) * 4 * kWgRows ? tc_sm_count() : ceil_div(r, 4 * kWgRows));
+}
+
+int tc_pair_wgrad(int64_t rows, const void* Ga, const void* Za, const void* Gb, const void* Zb, float* partial, int parts, cudaStream_t st) {
+  if (int rc = configure_kernels()) return rc;
+  WgradArgs wa{};
+  wa.G2 = static_cast<const __nv_bfloat16*>(Ga); wa.H2 = static_cast<const __nv_bfloat16*>(Za);
+  wa.G1 = static_cast<const __nv_bfloat16*>(Gb); wa.H1 = static_cast<const __nv_bfloat16*>(Zb);
+  wa.partial = partial; wa.n_z = 2; wa.accumulate = 0;
+  hgn_chunks none{};
+  const int64_t rpp = ceil_div(ceil_div(rows > 0 ? rows : 1, parts), kWgRows) * kWgRows;
+  const size_t wg_smem = size_t(kWgStages) * kWgStageBytes + 64;
+  HGN_TIMED("mlp_wgrad_tc", st);
+  mlp_wgrad_tc_kernel<<<dim3(unsigned(parts), 1), kWgThreads, wg_smem, st>>>(rows, 0, rows > 0 ? rows : 1, rpp, none, wa);
+  HGN_LAUNCH_OK("pair_wgrad_tc");
   return HGN_OK;
 }
 
@@ -788,7 +806,7 @@ static BwdLayoutTc bwd_layout_tc(int64_t rows, int n_chunks) {
   const int64_t cap = int64_t(1) << 21;                      // <= 2M rows per pass (6 x 512 MiB of bf16 workspace)
   L.slab_rows = rows < cap ? (rows > 0 ? rows : 1) : cap;
   L.slab_rows = ceil_div(L.slab_rows, kTile) * kTile;
-  L.parts = L.slab_rows >= int64_t(sm_count()) * 4 * kWgRows ? sm_count() : ceil_div(L.slab_rows, 4 * kWgRows);
+  L.parts = L.slab_rows >= int64_t(tc_sm_count()) * 4 * kWgRows ? tc_sm_count() : ceil_div(L.slab_rows, 4 * kWgRows);
   L.rows_per_part = ceil_div(ceil_div(L.slab_rows, L.parts), kWgRows) * kWgRows;
   L.groups = 1 + (n_chunks + 2) / 3;
   L.n_z = n_chunks + 2;
@@ -839,10 +857,10 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
     const int64_t this_rows = rows - slab0 < L.slab_rows ? rows - slab0 : L.slab_rows;
     if (this_rows > 0) {
       const int64_t tiles = ceil_div(this_rows, kTile);
-      const unsigned grid = unsigned(tiles < sm_count() ? tiles : sm_count());
+      const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
       HGN_TIMED("mlp_tile_tc_bwd", st);
       mlp_tile_tc_kernel<true><<<grid, kTileThreads, S.total, st>>>(rows, tiles, slab0, *ch, static_cast<const uint8_t*>(packed),
-                                                                    resident ? 1 : 0, nullptr, 0, nullptr, bw);
+                                                                    resident ? 1 : 0, nullptr, 0, nullptr, bw, PreAdd{});
       HGN_LAUNCH_OK("mlp_bwd_tc");
     }
     wa.accumulate = pass > 0;

@@ -82,6 +82,15 @@ class GraphNet(nn.Module):
         senders = segment_plan(to_device_index(edge_set.senders, v.device), num_nodes)
         receivers = segment_plan(to_device_index(edge_set.receivers, v.device), num_nodes)
         params = _mlp_parameters(model, 3 * v.shape[1], v)
+        if v.dtype == torch.bfloat16 and e.dtype == torch.bfloat16:
+            # throughput mode: node-side pre-projection + projected edge kernels; with the 'sum' aggregator the
+            # receiver-keyed aggregate is produced by the same autograd node (see ops._EdgeUpdate) and handed to
+            # _aggregates through the tensor it belongs to
+            want_agg = self.message_passing_aggregator == 'sum'
+            out, agg = ops.edge_update(params, _packed_cache(model), v, e, senders, receivers, want_agg)
+            if agg is not None:
+                out._hgn_sum_agg = (receivers, agg)
+            return out
         chunks = [ops.ChunkSpec(0, senders), ops.ChunkSpec(0, receivers), ops.ChunkSpec(1)]
         return ops.fused_mlp(params, _packed_cache(model), [v, e], chunks, rows=e.shape[0], resid_source=1)
 
@@ -96,6 +105,10 @@ class GraphNet(nn.Module):
             if edge_set.name not in names:      # graphnet.py:43
                 continue
             plan = segment_plan(to_device_index(edge_set.receivers, device), num_nodes)
+            ready = getattr(edge_set.features, '_hgn_sum_agg', None)
+            if ready is not None and reducers == ('sum',) and ready[0] is plan:
+                out.append(ready[1])
+                continue
             out.extend(ops.segment_aggregate(edge_set.features, plan, reducers))
         return out
 

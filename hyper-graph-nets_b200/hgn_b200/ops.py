@@ -282,6 +282,127 @@ def fused_mlp(params: Sequence[torch.Tensor], packed_cache: dict, sources: Seque
     return _FusedMLP.apply(call, *params, *sources)
 
 
+# ------------------------------------------------------------------------------------------------
+# projected edge update (bf16): node-side pre-projection + fused edge kernels (csrc/edge_tc.cu)
+# ------------------------------------------------------------------------------------------------
+class _NodeProjection(torch.autograd.Function):
+    """``Ps = v W0[:, 0:128]^T``, ``Pr = v W0[:, 128:256]^T`` -- the sender / receiver blocks of the edge MLP's first
+    linear (graphnet.py:28-31 concatenation order), applied once per node instead of once per edge."""
+
+    @staticmethod
+    def forward(ctx, v, W0, packed):
+        lib = _cabi.load()
+        n = v.shape[0]
+        ps = torch.empty((n, D_LATENT), dtype=v.dtype, device=v.device)
+        pr = torch.empty((n, D_LATENT), dtype=v.dtype, device=v.device)
+        with torch.cuda.device(v.device):
+            _cabi.check(lib.hgn_edge_project_forward(_cabi.HGN_BF16, n, v.data_ptr(), packed.data_ptr(), ps.data_ptr(), pr.data_ptr(),
+                                                     _cabi.stream_ptr()), "hgn_edge_project_forward")
+        _count()
+        ctx.save_for_backward(v)
+        ctx.packed = packed
+        ctx.w0_shape = tuple(W0.shape)
+        return ps, pr
+
+    @staticmethod
+    def backward(ctx, gs, gr):
+        lib = _cabi.load()
+        (v,) = ctx.saved_tensors
+        n = v.shape[0]
+        gs = gs.contiguous() if gs is not None else torch.zeros_like(v)
+        gr = gr.contiguous() if gr is not None else torch.zeros_like(v)
+        grad_v = torch.empty_like(v)
+        grad_w0 = torch.zeros(ctx.w0_shape, dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            ws_bytes = lib.hgn_edge_project_backward_workspace_bytes(_cabi.HGN_BF16, n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+            _cabi.check(lib.hgn_edge_project_backward(_cabi.HGN_BF16, n, v.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(),
+                                                      grad_v.data_ptr(), grad_w0.data_ptr(), ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
+                        "hgn_edge_project_backward")
+        _count(4)
+        return grad_v, grad_w0, None
+
+
+class _EdgeUpdate(torch.autograd.Function):
+    """``e' = e + LN(MLP(Ps[s] + Pr[r] + We e ...))`` and, when ``want_agg``, ``agg = segment_sum(e', receivers)``.
+    Returning the aggregate from the same node of the autograd graph lets the backward kernel gather its gradient
+    through ``receivers`` instead of materialising it as an ``[E,128]`` tensor and adding it to the next layer's."""
+
+    @staticmethod
+    def forward(ctx, ps, pr, e, W0, b0, W1, b1, W2, b2, gamma, beta, packed, s_plan, r_plan, want_agg):
+        lib = _cabi.load()
+        E = e.shape[0]
+        out = torch.empty_like(e)
+        with torch.cuda.device(e.device):
+            _cabi.check(lib.hgn_edge_update_forward(_cabi.HGN_BF16, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(),
+                                                    r_plan.ids32.data_ptr(), packed.data_ptr(), out.data_ptr(), _cabi.stream_ptr()),
+                        "hgn_edge_update_forward")
+            _count()
+            agg = None
+            if want_agg:
+                agg = torch.empty((r_plan.num_segments, D_LATENT), dtype=e.dtype, device=e.device)
+                _cabi.check(lib.hgn_segment_reduce(_cabi.HGN_BF16, out.data_ptr(), E, D_LATENT, r_plan.perm.data_ptr(), r_plan.rowptr.data_ptr(),
+                                                   r_plan.num_segments, agg.data_ptr(), None, None, None, None, None, 0, _cabi.stream_ptr()),
+                            "hgn_segment_reduce")
+                _count()
+        ctx.save_for_backward(ps, pr, e)
+        ctx.packed, ctx.s_plan, ctx.r_plan = packed, s_plan, r_plan
+        ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
+        if want_agg:
+            return out, agg
+        return out, None
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_agg):
+        lib = _cabi.load()
+        ps, pr, e = ctx.saved_tensors
+        s_plan, r_plan = ctx.s_plan, ctx.r_plan
+        E, dev = e.shape[0], e.device
+        n = ps.shape[0]
+        if grad_out is not None:
+            grad_out = grad_out.contiguous().to(e.dtype)
+        if grad_agg is not None:
+            grad_agg = grad_agg.contiguous().to(e.dtype)
+        grad_e = torch.empty_like(e)
+        g0 = torch.empty_like(e)
+        gparams = [torch.zeros(shape, dtype=torch.float32, device=dev) if i == 0 else torch.empty(shape, dtype=torch.float32, device=dev)
+                   for i, shape in enumerate(ctx.param_shapes)]
+        gs = torch.empty((n, D_LATENT), dtype=e.dtype, device=dev)
+        gr = torch.empty((n, D_LATENT), dtype=e.dtype, device=dev)
+        with torch.cuda.device(dev):
+            ws_bytes = lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_BF16, E)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.hgn_edge_update_backward(
+                _cabi.HGN_BF16, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
+                ctx.packed.data_ptr(), _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(),
+                *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_edge_update_backward")
+            _count(2)
+            # d loss / d Ps, d Pr: sender- and receiver-keyed segment sums of G0 (deterministic CSR passes)
+            for plan, dst in ((s_plan, gs), (r_plan, gr)):
+                _cabi.check(lib.hgn_segment_reduce(_cabi.HGN_BF16, g0.data_ptr(), E, D_LATENT, plan.perm.data_ptr(), plan.rowptr.data_ptr(),
+                                                   n, dst.data_ptr(), None, None, None, None, None, 0, _cabi.stream_ptr()),
+                            "hgn_segment_reduce")
+                _count()
+        return (gs, gr, grad_e, *gparams, None, None, None, None)
+
+
+def edge_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Tensor, e: torch.Tensor, s_plan: SegmentPlan,
+                r_plan: SegmentPlan, want_agg: bool):
+    """Projected bf16 edge update (graphnet.py:22-32).  Returns ``(e', agg)`` where ``agg`` is the receiver-keyed 'sum'
+    aggregate of ``e'`` when ``want_agg`` else ``None``."""
+    _cabi.require_cuda(v, e)
+    if v.dtype != torch.bfloat16 or e.dtype != torch.bfloat16:
+        raise _cabi.HgnError("edge_update is the bf16 tcgen05 path; fp32 features go through fused_mlp")
+    W0 = params[0]
+    if W0.shape != (D_LATENT, 3 * D_LATENT) or v.shape[-1] != D_LATENT or e.shape[-1] != D_LATENT:
+        raise _cabi.HgnError(f"edge_update is specialised for latent 128: W0 {tuple(W0.shape)}, v {tuple(v.shape)}, e {tuple(e.shape)}")
+    v, e = v.contiguous(), e.contiguous()
+    with torch.cuda.device(v.device):
+        packed = _pack_weights(packed_cache, torch.bfloat16, 3, params)
+    ps, pr = _NodeProjection.apply(v, W0, packed)
+    return _EdgeUpdate.apply(ps, pr, e, *params, packed, s_plan, r_plan, bool(want_agg))
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     """fp32 column sums of ``x[rows, D]`` (deterministic)."""
     lib = _cabi.load()

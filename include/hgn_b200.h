@@ -141,6 +141,39 @@ int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunks, const vo
                      float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- projected edge update (HGN_BF16 only; HGN_F32 returns HGN_ERR_UNSUPPORTED: use hgn_mlp_* there) --------
+ * The edge update of src/migration/graphnet.py:22-32 with the first linear split by input block,
+ * W0 = [Ws | Wr | We] (columns 0:128 | 128:256 | 256:384 of edge_models.<set>.0.layers.linear_0.weight):
+ *     proj_s = v Ws^T, proj_r = v Wr^T                     once per NODE  (hgn_edge_project_forward)
+ *     e'     = e + LN(W2 relu(W1 relu(proj_s[s] + proj_r[r] + We e + b0) + b1) + b2)     per edge
+ * which replaces index_select x2 + cat + the K=384 addmm by two 128-wide row gathers and a K=128 GEMM.
+ * `packed` is the hgn_mlp_pack blob of the edge MLP with n_chunks = 3.  senders/receivers: int32 [E]. */
+int hgn_edge_project_forward(int dtype, int64_t num_nodes, const void* v, const void* packed,
+                             void* proj_s, void* proj_r, void* stream);
+/* grad_v[N,128] = grad_s Ws + grad_r Wr ; grad_W0[128,384] columns 0:256 = [grad_s^T v | grad_r^T v] (columns
+ * 256:384 are left untouched), where grad_s / grad_r are the sender- / receiver-keyed segment sums of grad_pre0. */
+size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t num_nodes);
+int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed,
+                              const void* grad_s, const void* grad_r, void* grad_v, float* grad_W0,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
+                            const int32_t* senders, const int32_t* receivers, const void* packed, void* out,
+                            void* stream);
+/* Backward (activations recomputed).  The incoming gradient of e' is  grad_out[e] + grad_agg[receivers[e]] :
+ * grad_out[E,128] (may be NULL) is the dense part (next layer / loss), grad_agg[N,128] (may be NULL) the gradient
+ * of the 'sum' aggregate of e' over receivers (graphnet.py:50-70), gathered here instead of being expanded to
+ * [E,128] by a separate kernel.  Outputs: grad_edge[E,128] = d loss / d e (residual branch included);
+ * grad_pre0[E,128] = d loss / d (first-layer pre-activation), whose sender- and receiver-keyed segment sums are
+ * the inputs of hgn_edge_project_backward; grad_W0 columns 256:384 (= We) only; all other parameter gradients
+ * complete (fp32, overwritten, fixed-order reductions). */
+size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges);
+int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
+                             const int32_t* senders, const int32_t* receivers, const void* packed,
+                             const void* grad_out, const void* grad_agg, void* grad_edge, void* grad_pre0,
+                             float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
+                             float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- column sums ------------------------------------------------------------------------------
  * out[D] (fp32) = sum over rows of x[rows, D]; two-stage fixed-order reduction (LayerNorm beta / bias
  * gradients).  D must be a multiple of 4 and <= 1024. */

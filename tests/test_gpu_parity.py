@@ -266,3 +266,71 @@ def test_bf16_kernels_vs_bf16_emulation(rows, n_nodes):
     assert rel_l2(e.grad.float(), ef.grad) < 1e-2 and rel_l2(v.grad.float(), vf.grad) < 1e-2
     for a, b in zip(params, wr):
         assert rel_l2(a.grad, b.grad) < 1e-2
+
+
+def _bf16_emulated_projected_edge(v, e, s, r, w):
+    """torch fp32 arithmetic with the rounding points of the projected edge kernels (csrc/edge_tc.cu): bf16 operands,
+    bf16 per-node projection tables, bf16 H1/H2."""
+    W0, b0, W1, b1, W2, b2, g, b = w
+    rd = lambda t: t.to(torch.bfloat16).float()
+    ps = rd(v @ rd(W0[:, :128]).t())
+    pr = rd(v @ rd(W0[:, 128:256]).t())
+    h = torch.relu(ps[s] + pr[r] + e @ rd(W0[:, 256:]).t() + b0)
+    h = torch.relu(rd(h) @ rd(W1).t() + b1)
+    return e + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
+
+
+@pytest.mark.parametrize("want_agg", [False, True])
+@pytest.mark.parametrize("rows,n_nodes", [(1, 5), (63, 40), (128, 64), (129, 33), (1000, 300), (9282, 1600), (200000, 40000)])
+def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg):
+    """ops.edge_update (node projection + fused edge forward/backward kernels with the aggregate's gradient gathered in
+    the kernel) against torch arithmetic with the same rounding points, on ragged tile counts."""
+    torch.manual_seed(rows + int(want_agg))
+    w = _random_mlp_weights(3, 11)
+    params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+    params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+    s = torch.randint(0, n_nodes, (rows,), device="cuda")
+    r = torch.randint(0, n_nodes, (rows,), device="cuda")
+    v = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    e = torch.randn(rows, 128, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    gup = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
+    gagg = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
+    out, agg = ops.edge_update(params, {}, v, e, sp, rp, want_agg)
+    loss = (out.float() * gup.float()).sum()
+    if want_agg:
+        loss = loss + (agg.float() * gagg.float()).sum()
+    loss.backward()
+    wr = [p.detach().clone().requires_grad_(True) for p in params]
+    vf, ef = v.detach().float().requires_grad_(True), e.detach().float().requires_grad_(True)
+    ref = _bf16_emulated_projected_edge(vf, ef, s, r, wr)
+    ref_loss = (ref * gup.float()).sum()
+    if want_agg:
+        ref_agg = torch.zeros(n_nodes, 128, device="cuda").index_add_(0, r, ref)
+        ref_loss = ref_loss + (ref_agg * gagg.float()).sum()
+        assert rel_err(agg.float(), ref_agg) < 1e-2
+    ref_loss.backward()
+    assert rel_err(out.float(), ref) < 1e-2
+    assert rel_l2(e.grad.float(), ef.grad) < 1e-2 and rel_l2(v.grad.float(), vf.grad) < 1.5e-2
+    for a, b in zip(params, wr):
+        assert rel_l2(a.grad, b.grad) < 1.5e-2
+
+
+def test_projected_edge_update_is_deterministic():
+    torch.manual_seed(3)
+    w = _random_mlp_weights(3, 11)
+    s = torch.randint(0, 3000, (20000,), device="cuda")
+    r = torch.randint(0, 3000, (20000,), device="cuda")
+    sp, rp = segment_plan(s, 3000), segment_plan(r, 3000)
+    v0 = torch.randn(3000, 128, device="cuda").to(torch.bfloat16)
+    e0 = torch.randn(20000, 128, device="cuda").to(torch.bfloat16)
+    runs = []
+    for _ in range(2):
+        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+        v, e = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+        out, agg = ops.edge_update(params, {}, v, e, sp, rp, True)
+        (out.float().sum() + (agg.float() ** 2).sum()).backward()
+        runs.append([out.detach(), agg.detach(), v.grad, e.grad] + [p.grad for p in params])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
