@@ -22,6 +22,8 @@
 // TMEM (512 columns): chain accumulator [0,128) | dW2 [128,256) | dW1 [256,384) | dWe [384,512).
 // Nothing but d e and G0 (and per-CTA fp32 partials at the end) is written to HBM; the previous design wrote six
 // [E,128] workspaces per layer.  All reductions have a fixed order (per-CTA partials, then a sequential sum over CTAs).
+#include <stdlib.h>
+
 #include "tile_common.cuh"
 
 namespace hgn {
@@ -33,6 +35,32 @@ __device__ __forceinline__ uint32_t ld_shared32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void ld_shared128(uint32_t addr, uint32_t* w) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
+}
+// packed bf16 helpers (one SASS instruction each: F2FP.RELU.BF16.F32.PACK_AB, HFMA2.BF16_V2, HSET2 + HMUL2)
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t x, uint32_t y) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(y));
+  return d;
+}
+// g * [h > 0] per 16-bit half: ReLU backward against the stored activation
+__device__ __forceinline__ uint32_t relu_bwd_bf16x2(uint32_t g, uint32_t h) {
+  uint32_t d;
+  asm("{\n\t.reg .b32 m;\n\tset.gt.bf16x2.bf16x2 m, %2, %3;\n\tmul.rn.bf16x2 %0, %1, m;\n\t}" : "=r"(d) : "r"(g), "r"(h), "r"(0u));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+// 256-bit read-only load that allocates in L1: gathered table rows are shared by neighbouring edges of a tile
+__device__ __forceinline__ void ldg256_l1(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -205,7 +233,14 @@ struct EdgeBwdArgs {
   float* w_partial;                 // [grid][3][128][128]  z = 0: dWe, 1: dW1, 2: dW2
   float* epi_colpart;               // [grid][4][2][128]    beta, gamma partial column sums per lane quadrant
   float* prod_colpart;              // [grid][3][128]       db2, db1, db0
+  long long* timeline;              // development: clock64 stamps of block 0 ([tile][32]) when HGN_TC_ABLATE has bit 64
+  int ablate;                       // development switches (HGN_TC_ABLATE): 1 no table/gradient loads, 2 no HBM stores,
+                                    // 4 no LayerNorm-vector column sums, 8 no bias column sums, 16 no weight-gradient MMAs
 };
+
+__device__ __forceinline__ void stamp(const EdgeBwdArgs& a, int64_t t, int slot) {
+  if (a.timeline != nullptr && blockIdx.x == 0 && t < 8) a.timeline[t * 32 + slot] = clock64();
+}
 
 __global__ void __launch_bounds__(kEbThreads, 1)
 edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, EdgeBwdArgs a) {
@@ -262,6 +297,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     };
     // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..), lane l the column pair 2l, 2l+1
     auto colsum = [&](uint32_t base, float& s0, float& s1) {
+      if (a.ablate & 8) return;
       const uint32_t pbase = base + pw * kPanel + (lane & 3) * 4;
       float t0 = 0.f, t1 = 0.f;
 #pragma unroll 16
@@ -282,6 +318,14 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     }
     for (int64_t t = 0; t < my_tiles; ++t) {
       const uint32_t par = uint32_t(t) & 1;
+      if (t + 1 < my_tiles) {                                // pull the next tile's edge rows into L2 a whole tile ahead
+        const int64_t row0 = (blockIdx.x + (t + 1) * gridDim.x) * kTile;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t line = int64_t(ptid) * 4 + j;        // 256 lines of 128 B
+          if (row0 + (line >> 1) < rows) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.edge + (row0 + (line >> 1)) * kD + (line & 1) * 64));
+        }
+      }
       mbar_wait(&bars[kEbG + 0], par, 50);
       colsum(buf(3, t), cs[0][0], cs[0][1]);                 // dY
       mbar_arrive(&bars[kEbCs + 0]);
@@ -289,18 +333,19 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       colsum(buf(2, t), cs[1][0], cs[1][1]);                 // dH2'
       mbar_arrive(&bars[kEbCs + 1]);
       const bool more = t + 1 < my_tiles;
-      if (more) {
-        mbar_wait(&bars[kEbFree], par, 52);
-        load_e(t + 1);
-      }
-      mbar_wait(&bars[kEbG + 2], par, 53);
+      mbar_wait(&bars[kEbG + 2], par, 53);                   // E4 done: step 4 has completed and H1 has been read back, so
+      if (ptid == 0) stamp(a, t, 22);
+      if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) is free for the next tile's edge rows
+      if (ptid == 0) stamp(a, t, 23);
       colsum(buf(3, t), cs[2][0], cs[2][1]);                 // dH1'
       mbar_arrive(&bars[kEbCs + 2]);
+      if (ptid == 0) stamp(a, t, 24);
       if (more) {
         cp_async_wait<0>();
         fence_async_smem();
         mbar_arrive(&bars[kEbFull]);
       }
+      if (ptid == 0) stamp(a, t, 25);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -314,7 +359,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       const uint32_t acc = tmem_base, dW2 = tmem_base + 128, dW1 = tmem_base + 256, dWe = tmem_base + 384;
       uint32_t epi_phase = 0;
       auto wait_epi = [&]() {
-        mbar_wait(&bars[kEbEpi], epi_phase++ & 1, 60);
+        mbar_spin(&bars[kEbEpi], epi_phase++ & 1, 60);
         fence_after_sync();
       };
       auto chain = [&](uint32_t a_addr, uint32_t b_addr, bool b_mn) {      // acc = A[128 x 128] (K-major) * B
@@ -326,6 +371,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
       };
       auto wgrad = [&](uint32_t d, uint32_t g_addr, uint32_t z_addr, bool first) {   // d (+)= G^T Z over the tile's 128 rows
+        if (a.ablate & 16) return;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           mma_ss(d, sdesc_mnmajor(g_addr + ks * 2048, kPanel), sdesc_mnmajor(z_addr + ks * 2048, kPanel), id_mm, !(first && ks == 0));
@@ -335,27 +381,35 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         const bool first = t == 0;
         mbar_wait(&bars[kEbFull], uint32_t(t) & 1, 61);
         fence_after_sync();
+        stamp(a, t, 0);
         if (!first) wait_epi();                                  // previous tile's last epilogue has drained the accumulator
+        stamp(a, t, 1);
         chain(S, sbase + kEbWe, false);  mma_commit(&bars[kEbAcc]);                                    // 0: e We^T
-        wait_epi(); chain(A, sbase + kEbW1, false);  mma_commit(&bars[kEbAcc]);                        // 1: H1 W1^T
-        wait_epi(); chain(B, sbase + kEbW2, false);  mma_commit(&bars[kEbAcc]);                        // 2: H2 W2^T
-        wait_epi(); chain(C, sbase + kEbW2, true);   wgrad(dW2, C, B, first); mma_commit(&bars[kEbAcc]);   // 3: dY W2 ; dW2
-        wait_epi(); chain(B, sbase + kEbW1, true);   wgrad(dW1, B, A, first); mma_commit(&bars[kEbAcc]);   // 4: dH2' W1 ; dW1
-        mma_commit(&bars[kEbFree]);
-        wait_epi(); chain(C, sbase + kEbWe, true);   wgrad(dWe, C, S, first); mma_commit(&bars[kEbAcc]);   // 5: dH1' We ; dWe
+        stamp(a, t, 2);
+        wait_epi(); stamp(a, t, 3); chain(A, sbase + kEbW1, false);  mma_commit(&bars[kEbAcc]);                        // 1: H1 W1^T
+        wait_epi(); stamp(a, t, 4); chain(B, sbase + kEbW2, false);  mma_commit(&bars[kEbAcc]);                        // 2: H2 W2^T
+        wait_epi(); stamp(a, t, 5); chain(C, sbase + kEbW2, true);   wgrad(dW2, C, B, first); mma_commit(&bars[kEbAcc]);   // 3: dY W2 ; dW2
+        wait_epi(); stamp(a, t, 6); chain(B, sbase + kEbW1, true);   wgrad(dW1, B, A, first); mma_commit(&bars[kEbAcc]);   // 4: dH2' W1 ; dW1
+        wait_epi(); stamp(a, t, 7); chain(C, sbase + kEbWe, true);   wgrad(dWe, C, S, first); mma_commit(&bars[kEbAcc]);   // 5: dH1' We ; dWe
+        stamp(a, t, 8);
       }
     }
   } else {
     // =============================== epilogue ============================================================
+    // Instruction-lean on purpose (the phases below sit on the serial critical path of a tile and the FP32 pipes issue one
+    // warp instruction per two cycles): packed fp32x2 arithmetic, convert+ReLU+pack in one instruction, ReLU backward as
+    // HSET2/HMUL2 against the activation words still sitting in shared memory (no mask registers), table / gradient rows
+    // fetched a phase ahead, and the warp column-sum butterflies run in the shadow of the MMA steps.
     const int q = warp & 3, hh = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t acc = tmem_base + lane_addr + hh * 64;
-    const float *b0 = prm + hh * 64, *b1 = prm + kD + hh * 64, *b2 = prm + 2 * kD + hh * 64, *gam = prm + 3 * kD + hh * 64;
+    const float2 *b0 = reinterpret_cast<const float2*>(prm + hh * 64), *b1 = reinterpret_cast<const float2*>(prm + kD + hh * 64),
+                 *b2 = reinterpret_cast<const float2*>(prm + 2 * kD + hh * 64), *gam = reinterpret_cast<const float2*>(prm + 3 * kD + hh * 64);
     uint32_t acc_phase = 0;
     float cbeta[2] = {0.f, 0.f}, cgamma[2] = {0.f, 0.f};
     auto wait_acc = [&](int tag) {
-      mbar_wait(&bars[kEbAcc], acc_phase++ & 1, tag);
+      mbar_spin(&bars[kEbAcc], acc_phase++ & 1, tag);
       fence_after_sync();
     };
     // k-th column-sum hand-over of (local) tile tt: the producers have finished reading that tile from its buffer
@@ -366,217 +420,258 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       mbar_arrive(&bars[kEbEpi]);
       if (producers_k >= 0) mbar_arrive(&bars[kEbG + producers_k]);
     };
-    auto store_cg = [&](uint32_t bufaddr, int cg, const uint32_t* w) {      // 32 columns (16 packed words) of row r
-      const uint32_t rowbase = bufaddr + hh * kPanel;
+    const uint32_t row_off = hh * kPanel;                      // my 64 columns = panel hh of every buffer
+    auto store_row = [&](uint32_t bufaddr, const uint32_t* w) {   // 64 columns (32 packed words) of row r
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st_shared128(rowbase + sw128_chunk(r, cg * 4 + k), w + 4 * k);
+      for (int k = 0; k < 8; ++k) st_shared128(bufaddr + row_off + sw128_chunk(r, k), w + 4 * k);
     };
+    auto load_row = [&](uint32_t bufaddr, uint32_t* w) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ld_shared128(bufaddr + row_off + sw128_chunk(r, k), w + 4 * k);
+    };
+    auto tile_row = [&](int64_t tt) { return (blockIdx.x + tt * gridDim.x) * kTile + r; };
+    auto load_tables = [&](int64_t si, int64_t ri, uint32_t* pq) {          // Ps[s] and Pr[r]: my 64 columns of each
+      const __nv_bfloat16* psrow = a.proj_s + si * kD + hh * 64;
+      const __nv_bfloat16* prrow = a.proj_r + ri * kD + hh * 64;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ldg256_l1(psrow + 16 * k, pq + 8 * k); ldg256_l1(prrow + 16 * k, pq + 32 + 8 * k); }
+    };
+    const bool ld_on = !(a.ablate & 1);
+    // software pipeline across tiles: the indices of the NEXT tile are read during the current one and its table rows pulled
+    // into L2 (prefetch, no registers); the register loads are issued one MMA step ahead of their use
+    auto prefetch_l2 = [&](const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); };
+    int64_t si = 0, ri = 0;
+    if (my_tiles > 0) {
+      const int64_t g0 = tile_row(0);
+      if (g0 < rows) { si = __ldg(a.senders + g0); ri = __ldg(a.receivers + g0); }
+    }
     for (int64_t t = 0; t < my_tiles; ++t) {
       const uint32_t A = buf(1, t), B = buf(2, t), C = buf(3, t);
       // row-half exchange area (LayerNorm statistics): the first 4 KiB of buffer C, which is idle until dY is written into it
       float2* xch = reinterpret_cast<float2*>(smem + (C - sbase));
-      const int64_t grow = (blockIdx.x + t * gridDim.x) * kTile + r;
+      const int64_t grow = tile_row(t);
       const bool valid = grow < rows;
-      const int64_t si = valid ? __ldg(a.senders + grow) : 0, ri = valid ? __ldg(a.receivers + grow) : 0;
-      uint32_t mask1[2], mask2[2];
+      const int64_t ri_cur = ri;
+      const int64_t gnext = tile_row(t + 1);
+      const bool vnext = t + 1 < my_tiles && gnext < rows;
+      int32_t si_n = 0, ri_n = 0;
+      if (vnext) { si_n = __ldg(a.senders + gnext); ri_n = __ldg(a.receivers + gnext); }   // consumed after E2
+      const bool has_do = valid && a.grad_out != nullptr && ld_on, has_ga = valid && a.grad_agg != nullptr && ld_on;
+      const __nv_bfloat16* dorow = a.grad_out + grow * kD + hh * 64;
+      const __nv_bfloat16* garow = a.grad_agg + ri_cur * kD + hh * 64;
       // ---- E0: H1 = relu(e We^T + Ps[s] + Pr[r] + b0) -> A ---------------------------------------------------
       {
-        const __nv_bfloat16* psrow = a.proj_s + si * kD + hh * 64;
-        const __nv_bfloat16* prrow = a.proj_r + ri * kD + hh * 64;
-        uint32_t pq[32], pn[32];
-        ldg256(psrow, pq); ldg256(psrow + 16, pq + 8); ldg256(prrow, pq + 16); ldg256(prrow + 16, pq + 24);
+        uint32_t pq[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) pq[j] = 0u;
+        if (ld_on) load_tables(si, ri, pq);
+        if (has_do) prefetch_l2(dorow);
+        if (has_ga) prefetch_l2(garow);
         if (t > 0) wait_cs(1, t - 1);                           // the producers' dH2' column sum has left this buffer
-        wait_acc(100);
+        wait_acc(100); if (tid == 0) stamp(a, t, 10);
+        uint32_t h[32];
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
-          if (cg == 0) { ldg256(psrow + 32, pn); ldg256(psrow + 48, pn + 8); ldg256(prrow + 32, pn + 16); ldg256(prrow + 48, pn + 24); }
           tmem_ld_wait();
-          const uint32_t* pp = cg == 0 ? pq : pn;
-          uint32_t h[16], m = 0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = cg * 32 + 2 * j;
-            const float x0 = fmaxf(__uint_as_float(v[2 * j]) + bf16_lo(pp[j]) + bf16_lo(pp[16 + j]) + b0[col], 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bf16_hi(pp[j]) + bf16_hi(pp[16 + j]) + b0[col + 1], 0.f);
-            h[j] = pack_bf16(x0, x1);
-            m |= (x0 > 0.f ? (1u << (2 * j)) : 0u) | (x1 > 0.f ? (1u << (2 * j + 1)) : 0u);
+            float2 x = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            x = __fadd2_rn(x, unpack_bf16x2(pq[cg * 16 + j]));
+            x = __fadd2_rn(x, unpack_bf16x2(pq[32 + cg * 16 + j]));
+            x = __fadd2_rn(x, b0[cg * 16 + j]);
+            h[cg * 16 + j] = cvt_relu_bf16x2(x.x, x.y);
           }
-          mask1[cg] = m;
-          store_cg(A, cg, h);
         }
+        store_row(A, h);
+        if (tid == 0) stamp(a, t, 11);
         done(-1);
       }
-      // ---- E1: H2 = relu(H1 W1^T + b1) -> B -----------------------------------------------------------------------
+      // dO = grad_out[row] + grad_agg[receiver]: requested two phases before its first use
+      uint32_t dreg[32];
       {
+        uint32_t dq[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) dq[j] = 0u;
+        if (has_do) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ldg256(dorow + 16 * k, dq + 8 * k);
+        }
+        if (has_ga) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ldg256_l1(garow + 16 * k, dq + 32 + 8 * k);
+        }
+        // ---- E1: H2 = relu(H1 W1^T + b1) -> B -------------------------------------------------------------------
         if (t > 0) wait_cs(2, t - 1);                           // previous tile's dH1' column sum has left this buffer
-        wait_acc(101);
+        wait_acc(101); if (tid == 0) stamp(a, t, 12);
+        uint32_t h[32];
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          uint32_t h[16], m = 0;
+          if (tid == 0) stamp(a, t, 26 + 2 * cg);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = cg * 32 + 2 * j;
-            const float x0 = fmaxf(__uint_as_float(v[2 * j]) + b1[col], 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + b1[col + 1], 0.f);
-            h[j] = pack_bf16(x0, x1);
-            m |= (x0 > 0.f ? (1u << (2 * j)) : 0u) | (x1 > 0.f ? (1u << (2 * j + 1)) : 0u);
+            const float2 x = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b1[cg * 16 + j]);
+            h[cg * 16 + j] = cvt_relu_bf16x2(x.x, x.y);
           }
-          mask2[cg] = m;
-          store_cg(B, cg, h);
+          if (tid == 0) stamp(a, t, 27 + 2 * cg);
         }
+        store_row(B, h);
+        if (tid == 0) stamp(a, t, 13);
         done(-1);
+        // the gradient rows have landed by now: one rounding to bf16, the value every later use sees
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dreg[j] = add_bf16x2(dq[j], dq[32 + j]);
       }
       // ---- E2: y = H2 W2^T + b2 ; LayerNorm forward statistics and backward -> dY -> C --------------------------------
-      uint32_t dreg[32];                                        // dO = grad_out[row] + grad_agg[receiver] of my 64 columns, bf16
+      uint32_t preg[32];                                        // dO * yhat (bf16): gamma-gradient terms, summed after the phase
       {
-        const __nv_bfloat16* dorow = a.grad_out + grow * kD + hh * 64;
-        const __nv_bfloat16* garow = a.grad_agg + ri * kD + hh * 64;
-        const bool has_do = valid && a.grad_out != nullptr, has_ga = valid && a.grad_agg != nullptr;
-        uint32_t dq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dq[j] = 0u;
-        if (has_do) { ldg256(dorow, dq); ldg256(dorow + 16, dq + 8); }
-        if (has_ga) { ldg256(garow, dq + 16); ldg256(garow + 16, dq + 24); }
-        wait_acc(102);
-        // statistics of my 64 columns, merged with the other half of the row (Chan's parallel update, equal counts)
-        float s = 0.f;
-#pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
+        wait_acc(102); if (tid == 0) stamp(a, t, 14);
+        float2 y[32];
+        {
           uint32_t v[32];
-          tmem_ld32(acc + cg * 32, v);
+          tmem_ld32(acc, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + b2[cg * 32 + j];
-        }
-        const float mean_h = s * (1.0f / 64.0f);
-        float m2h = 0.f;
-#pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
-          tmem_ld32(acc + cg * 32, v);
+          for (int j = 0; j < 16; ++j) y[j] = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2[j]);
+          tmem_ld32(acc + 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(v[j]) + b2[cg * 32 + j] - mean_h; m2h = fmaf(d, d, m2h); }
+          for (int j = 0; j < 16; ++j) y[16 + j] = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), b2[16 + j]);
         }
+        // statistics of my 64 columns (shifted by the first value), merged with the other half of the row (Chan's update)
+        const float c0 = y[0].x;
+        const float2 nc = make_float2(-c0, -c0);
+        float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 d0 = __fadd2_rn(y[j], nc), d1 = __fadd2_rn(y[j + 1], nc);
+          s1a = __fadd2_rn(s1a, d0); s1b = __fadd2_rn(s1b, d1);
+          s2a = __ffma2_rn(d0, d0, s2a); s2b = __ffma2_rn(d1, d1, s2b);
+        }
+        const float s1 = (s1a.x + s1a.y) + (s1b.x + s1b.y), s2 = (s2a.x + s2a.y) + (s2b.x + s2b.y);
+        const float mean_h = c0 + s1 * (1.0f / 64.0f);
+        const float m2h = s2 - s1 * s1 * (1.0f / 64.0f);
         xch[hh * kTile + r] = make_float2(mean_h, m2h);
         epi_bar_sync();
         const float2 oth = xch[(1 - hh) * kTile + r];
         const float mean = 0.5f * (mean_h + oth.x);
         const float dm = mean_h - oth.x;
-        const float rstd = rsqrtf((m2h + oth.y + 32.0f * dm * dm) * (1.0f / kD) + kEps);
-        float m1 = 0.f, m2 = 0.f;
+        const float rstd = rsqrtf(fmaxf(m2h + oth.y + 32.0f * dm * dm, 0.f) * (1.0f / kD) + kEps);
+        const float2 rs2 = make_float2(rstd, rstd), nm2 = make_float2(-mean * rstd, -mean * rstd);
+        float2 m1a = make_float2(0.f, 0.f), m2a = m1a;
 #pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
-          tmem_ld32(acc + cg * 32, v);
-          // dO of this column group, rounded to bf16 once (the value every later use sees); then the loads of the next group
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            dreg[cg * 16 + j] = pack_bf16(bf16_lo(dq[j]) + bf16_lo(dq[16 + j]), bf16_hi(dq[j]) + bf16_hi(dq[16 + j]));
-          if (cg == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dq[j] = 0u;
-            if (has_do) { ldg256(dorow + 32, dq); ldg256(dorow + 48, dq + 8); }
-            if (has_ga) { ldg256(garow + 32, dq + 16); ldg256(garow + 48, dq + 24); }
-          }
-          tmem_ld_wait();
-          float p[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float dj = (j & 1) ? bf16_hi(dreg[cg * 16 + (j >> 1)]) : bf16_lo(dreg[cg * 16 + (j >> 1)]);
-            const float yh = (__uint_as_float(v[j]) + b2[cg * 32 + j] - mean) * rstd;
-            const float z = dj * gam[cg * 32 + j];
-            m1 += z;
-            m2 = fmaf(z, yh, m2);
-            p[j] = dj * yh;
-          }
-          cgamma[cg] += warp_colsum32(p, lane);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) p[j] = (j & 1) ? bf16_hi(dreg[cg * 16 + (j >> 1)]) : bf16_lo(dreg[cg * 16 + (j >> 1)]);
-          cbeta[cg] += warp_colsum32(p, lane);
+        for (int j = 0; j < 32; ++j) {
+          y[j] = __ffma2_rn(y[j], rs2, nm2);                    // yhat
+          const float2 d = unpack_bf16x2(dreg[j]);
+          const float2 z = __fmul2_rn(d, gam[j]);
+          m1a = __fadd2_rn(m1a, z);
+          m2a = __ffma2_rn(z, y[j], m2a);
+          const float2 p = __fmul2_rn(d, y[j]);
+          preg[j] = pack_bf16(p.x, p.y);
         }
-        xch[2 * kTile + hh * kTile + r] = make_float2(m1, m2);
+        xch[2 * kTile + hh * kTile + r] = make_float2(m1a.x + m1a.y, m2a.x + m2a.y);
         epi_bar_sync();
         const float2 o2 = xch[2 * kTile + (1 - hh) * kTile + r];
-        m1 = (m1 + o2.x) * (1.0f / kD);
-        m2 = (m2 + o2.y) * (1.0f / kD);
-        epi_bar_sync();                                         // every thread has read both exchanges: dY may overwrite them
+        const float m1 = (m1a.x + m1a.y + o2.x) * (1.0f / kD), m2 = (m2a.x + m2a.y + o2.y) * (1.0f / kD);
+        const float2 nm1 = make_float2(-m1, -m1), nmm2 = make_float2(-m2, -m2);
+        uint32_t o[32];
 #pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
-          tmem_ld32(acc + cg * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = cg * 32 + 2 * j;
-            const float yh0 = (__uint_as_float(v[2 * j]) + b2[col] - mean) * rstd;
-            const float yh1 = (__uint_as_float(v[2 * j + 1]) + b2[col + 1] - mean) * rstd;
-            const float dy0 = rstd * (bf16_lo(dreg[cg * 16 + j]) * gam[col] - m1 - yh0 * m2);
-            const float dy1 = rstd * (bf16_hi(dreg[cg * 16 + j]) * gam[col + 1] - m1 - yh1 * m2);
-            o[j] = pack_bf16(dy0, dy1);
-          }
-          store_cg(C, cg, o);
+        for (int j = 0; j < 32; ++j) {
+          const float2 z = __fmul2_rn(unpack_bf16x2(dreg[j]), gam[j]);
+          const float2 u = __fmul2_rn(__ffma2_rn(y[j], nmm2, __fadd2_rn(z, nm1)), rs2);     // rstd (dO gamma - m1 - yhat m2)
+          o[j] = pack_bf16(u.x, u.y);
         }
+        epi_bar_sync();                                         // every thread has read both exchanges: dY may overwrite them
+        store_row(C, o);
+        if (tid == 0) stamp(a, t, 15);
         done(0);
       }
+      // (in the shadow of MMA step 3) gamma gradient: column sums of dO * yhat over this warp's 32 rows
+      if (!(a.ablate & 4)) {
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { p[2 * j] = bf16_lo(preg[cg * 16 + j]); p[2 * j + 1] = bf16_hi(preg[cg * 16 + j]); }
+          cgamma[cg] += warp_colsum32(p, lane);
+        }
+      }
+      // indices of the next tile (their table rows are requested one phase later)
+      si = si_n; ri = ri_n;
+      if (vnext && ld_on) { prefetch_l2(a.proj_s + si * kD + hh * 64); prefetch_l2(a.proj_r + ri * kD + hh * 64); }
       // ---- E3: dH2' = (dY W2) * [H2 > 0] -> B ---------------------------------------------------------------------
       {
-        wait_acc(103);
+        wait_acc(103); if (tid == 0) stamp(a, t, 16);
+        uint32_t hw[32], o[32];
+        load_row(B, hw);                                        // H2, about to be replaced by its own gradient
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          const uint32_t m = mask2[cg];
-          uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            o[j] = pack_bf16((m >> (2 * j)) & 1u ? __uint_as_float(v[2 * j]) : 0.f, (m >> (2 * j + 1)) & 1u ? __uint_as_float(v[2 * j + 1]) : 0.f);
-          store_cg(B, cg, o);
+            o[cg * 16 + j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[cg * 16 + j]);
         }
+        store_row(B, o);
+        if (tid == 0) stamp(a, t, 17);
         done(1);
+      }
+      // (in the shadow of MMA step 4) beta gradient: column sums of dO
+      if (!(a.ablate & 4)) {
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { p[2 * j] = bf16_lo(dreg[cg * 16 + j]); p[2 * j + 1] = bf16_hi(dreg[cg * 16 + j]); }
+          cbeta[cg] += warp_colsum32(p, lane);
+        }
       }
       // ---- E4: G0 = dH1' = (dH2' W1) * [H1 > 0] -> C and -> HBM -----------------------------------------------------------
       {
         wait_cs(0, t);                                          // the producers' dY column sum has left buffer C
-        wait_acc(104);
-        __nv_bfloat16* g0row = a.grad_pre0 + (valid ? grow : 0) * kD + hh * 64;
+        wait_acc(104); if (tid == 0) stamp(a, t, 18);
+        uint32_t hw[32], o[32];
+        load_row(A, hw);                                        // H1 (its buffer is refilled only after this phase)
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          const uint32_t m = mask1[cg];
-          uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            o[j] = pack_bf16((m >> (2 * j)) & 1u ? __uint_as_float(v[2 * j]) : 0.f, (m >> (2 * j + 1)) & 1u ? __uint_as_float(v[2 * j + 1]) : 0.f);
-          store_cg(C, cg, o);
-          if (valid) { stg256(g0row + cg * 32, o); stg256(g0row + cg * 32 + 16, o + 8); }
+            o[cg * 16 + j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[cg * 16 + j]);
         }
+        store_row(C, o);
+        if (tid == 0) stamp(a, t, 19);
         done(2);
+        if (valid && !(a.ablate & 2)) {
+          __nv_bfloat16* g0row = a.grad_pre0 + grow * kD + hh * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) stg256(g0row + 16 * k, o + 8 * k);
+        }
       }
       // ---- E5: d e = dH1' We + dO -> HBM -------------------------------------------------------------------------------
       {
-        wait_acc(105);
+        wait_acc(105); if (tid == 0) stamp(a, t, 20);
         __nv_bfloat16* derow = a.grad_edge + (valid ? grow : 0) * kD + hh * 64;
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
+          uint32_t v[32], o[16];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o[j] = pack_bf16(__uint_as_float(v[2 * j]) + bf16_lo(dreg[cg * 16 + j]), __uint_as_float(v[2 * j + 1]) + bf16_hi(dreg[cg * 16 + j]));
-          if (valid) { stg256(derow + cg * 32, o); stg256(derow + cg * 32 + 16, o + 8); }
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), unpack_bf16x2(dreg[cg * 16 + j]));
+            o[j] = pack_bf16(x.x, x.y);
+          }
+          if (valid && !(a.ablate & 2)) { stg256(derow + cg * 32, o); stg256(derow + cg * 32 + 16, o + 8); }
         }
+        if (tid == 0) stamp(a, t, 21);
         done(-1);
       }
     }
@@ -762,12 +857,29 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
   a.w_partial = reinterpret_cast<float*>(ws + L.w_partial);
   a.epi_colpart = reinterpret_cast<float*>(ws + L.epi);
   a.prod_colpart = reinterpret_cast<float*>(ws + L.prod);
+  { const char* ab = getenv("HGN_TC_ABLATE"); a.ablate = ab ? atoi(ab) : 0; }
+  static long long* tl_dev = nullptr;
+  if (a.ablate & 64) {
+    if (tl_dev == nullptr) cudaMalloc(&tl_dev, 8 * 32 * sizeof(long long));
+    cudaMemsetAsync(tl_dev, 0, 8 * 32 * sizeof(long long), st);
+    a.timeline = tl_dev;
+  }
   const int64_t tiles = ceil_div(num_edges, kTile);
   {
     HGN_TIMED("edge_bwd_tc", st);
     edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(num_edges, tiles, static_cast<const uint8_t*>(packed), a);
   }
   HGN_LAUNCH_OK("edge_bwd_tc");
+  if (a.timeline != nullptr) {
+    long long h[8 * 32];
+    cudaMemcpyAsync(h, a.timeline, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (int t = 0; t < 8; ++t) {
+      fprintf(stderr, "tile %d:", t);
+      for (int k = 0; k < 30; ++k) fprintf(stderr, " %lld", h[t * 32 + k] ? h[t * 32 + k] - h[0] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   {
     HGN_TIMED("reduce_weight_partials", st);
     edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, gW0, gW1, gW2,

@@ -140,6 +140,15 @@ __device__ __forceinline__ void debug_record(uint32_t tag, uint32_t a, uint32_t 
     __threadfence_system();
   }
 }
+// Busy-polling variant (test_wait never suspends the thread): lower wake-up latency for waits on a kernel's serial
+// critical path, at the price of issue slots -- use only where the waiting warp has nothing else to do.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    if (mbar_test(bar, parity)) return;
+  }
+  debug_record(uint32_t(tag), parity, 1, 0, 0, 0, 0);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   for (uint32_t spin = 0; spin < (1u << 23); ++spin) {
     if (mbar_try_wait(bar, parity)) return;
