@@ -222,7 +222,7 @@ constexpr uint32_t kEbBars = kEbParams + 5 * kD * 4;
 constexpr uint32_t kEbSmem = kEbBars + 128;                        // 232 064 B of the 232 448 available
 // kEbG + k / kEbCs + k (k = 0 dY, 1 dH2', 2 dH1'): one barrier per tile-in-buffer hand-over, so each completes exactly one
 // phase per tile and no waiter can fall two phases behind (a parity wait cannot tell phase n from phase n + 2)
-enum { kEbFull = 0, kEbFree = 1, kEbAcc = 2, kEbEpi = 3, kEbG = 4, kEbCs = 7, kEbTmem = 10 };
+enum { kEbFull = 0, kEbFree = 1, kEbAcc = 2, kEbEpi = 3, kEbG = 4, kEbCs = 7, kEbTmem = 10, kEbAfree = 11 };
 
 struct EdgeBwdArgs {
   const __nv_bfloat16 *edge, *proj_s, *proj_r;
@@ -239,7 +239,7 @@ struct EdgeBwdArgs {
 };
 
 __device__ __forceinline__ void stamp(const EdgeBwdArgs& a, int64_t t, int slot) {
-  if (a.timeline != nullptr && blockIdx.x == 0 && t < 8) a.timeline[t * 32 + slot] = clock64();
+  if (a.timeline != nullptr && blockIdx.x == 0 && t < 8) a.timeline[t * 48 + slot] = clock64();
 }
 
 __global__ void __launch_bounds__(kEbThreads, 1)
@@ -264,6 +264,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       mbar_init(&bars[kEbFree], 1);
       mbar_init(&bars[kEbAcc], 1);
       mbar_init(&bars[kEbEpi], kEbEpiThreads);
+      mbar_init(&bars[kEbAfree], kEbEpiThreads);
       for (int k = 0; k < 3; ++k) { mbar_init(&bars[kEbG + k], kEbEpiThreads); mbar_init(&bars[kEbCs + k], kEbProdThreads); }
       mbar_init_fence();
     }
@@ -295,21 +296,29 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       }
       cp_async_commit();
     };
-    // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..), lane l the column pair 2l, 2l+1
-    auto colsum = [&](uint32_t base, float& s0, float& s1) {
+    // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..); lane l reads the 16-byte piece l & 7
+    // (8 columns) of rows 4 i + (l >> 3).  Each lane keeps fp32 partials over ALL its tiles; the four row groups are
+    // combined once, after the last tile (fixed order).
+    float cs[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[k][j] = 0.f;
+    auto colsum = [&](uint32_t base, float (&acc8)[8]) {
       if (a.ablate & 8) return;
-      const uint32_t pbase = base + pw * kPanel + (lane & 3) * 4;
-      float t0 = 0.f, t1 = 0.f;
-#pragma unroll 16
-      for (int row = 0; row < kTile; ++row) {
-        const uint32_t w = ld_shared32(pbase + (row >> 3) * 1024 + (row & 7) * 128 + ((((lane >> 2) ^ (row & 7)) & 7) << 4));
-        t0 += bf16_lo(w);
-        t1 += bf16_hi(w);
+      const uint32_t pbase = base + pw * kPanel;
+      const int c = lane & 7, ro = lane >> 3;
+      float2 t[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        uint32_t w[4];
+        ld_shared128(pbase + sw128_chunk(4 * i + ro, c), w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = __fadd2_rn(t[j], unpack_bf16x2(w[j]));
       }
-      s0 += t0;
-      s1 += t1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc8[2 * j] += t[j].x; acc8[2 * j + 1] += t[j].y; }
     };
-    float cs[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     if (my_tiles > 0) {
       load_e(0);
       cp_async_wait<0>();
@@ -318,39 +327,61 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     }
     for (int64_t t = 0; t < my_tiles; ++t) {
       const uint32_t par = uint32_t(t) & 1;
-      if (t + 1 < my_tiles) {                                // pull the next tile's edge rows into L2 a whole tile ahead
+      const bool more = t + 1 < my_tiles;
+      if (more && !(a.ablate & 33)) {
+        // everything tile t+1 will read from HBM is pulled into L2 a whole tile ahead, by these otherwise idle warps (never
+        // by the epilogue warps: their proxy fences wait for outstanding prefetches): edge rows, dense gradient rows, and --
+        // through the tile's sender / receiver indices -- the rows of the two node tables and of the aggregate gradient
         const int64_t row0 = (blockIdx.x + (t + 1) * gridDim.x) * kTile;
+        auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); };
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t line = int64_t(ptid) * 4 + j;        // 256 lines of 128 B
-          if (row0 + (line >> 1) < rows) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.edge + (row0 + (line >> 1)) * kD + (line & 1) * 64));
+        for (int j = 0; j < 2; ++j) {
+          const int64_t grow = row0 + ptid + 64 * j;
+          if (grow < rows) {
+            const int64_t si = __ldg(a.senders + grow), ri = __ldg(a.receivers + grow);
+            pf(a.edge + grow * kD); pf(a.edge + grow * kD + 64);
+            if (a.grad_out != nullptr) { pf(a.grad_out + grow * kD); pf(a.grad_out + grow * kD + 64); }
+            pf(a.proj_s + si * kD); pf(a.proj_s + si * kD + 64);
+            pf(a.proj_r + ri * kD); pf(a.proj_r + ri * kD + 64);
+            if (a.grad_agg != nullptr) { pf(a.grad_agg + ri * kD); pf(a.grad_agg + ri * kD + 64); }
+          }
         }
       }
       mbar_wait(&bars[kEbG + 0], par, 50);
-      colsum(buf(3, t), cs[0][0], cs[0][1]);                 // dY
+      colsum(buf(3, t), cs[0]);                              // dY
       mbar_arrive(&bars[kEbCs + 0]);
       mbar_wait(&bars[kEbG + 1], par, 51);
-      colsum(buf(2, t), cs[1][0], cs[1][1]);                 // dH2'
+      colsum(buf(2, t), cs[1]);                              // dH2'
       mbar_arrive(&bars[kEbCs + 1]);
-      const bool more = t + 1 < my_tiles;
-      mbar_wait(&bars[kEbG + 2], par, 53);                   // E4 done: step 4 has completed and H1 has been read back, so
+      mbar_wait(&bars[kEbAfree], par, 52);                   // step 4 has completed and every epilogue thread has read H1 back:
       if (ptid == 0) stamp(a, t, 22);
-      if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) is free for the next tile's edge rows
+      if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) takes the next tile's edge rows
       if (ptid == 0) stamp(a, t, 23);
-      colsum(buf(3, t), cs[2][0], cs[2][1]);                 // dH1'
-      mbar_arrive(&bars[kEbCs + 2]);
-      if (ptid == 0) stamp(a, t, 24);
-      if (more) {
+      mbar_wait(&bars[kEbG + 2], par, 53);                   // dH1' is in buffer C
+      if (more) {                                            // publish the edge rows first: the next tile's step 0 waits on them
         cp_async_wait<0>();
         fence_async_smem();
         mbar_arrive(&bars[kEbFull]);
       }
+      if (ptid == 0) stamp(a, t, 24);
+      colsum(buf(3, t), cs[2]);                              // dH1'
+      mbar_arrive(&bars[kEbCs + 2]);
       if (ptid == 0) stamp(a, t, 25);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      float2 v = make_float2(cs[k][0], cs[k][1]);
-      *reinterpret_cast<float2*>(a.prod_colpart + (int64_t(blockIdx.x) * 3 + k) * kD + pw * 64 + lane * 2) = v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = cs[k][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        cs[k][j] = v;
+      }
+      if (lane < 8) {
+        float* dst = a.prod_colpart + (int64_t(blockIdx.x) * 3 + k) * kD + pw * 64 + lane * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(cs[k][0], cs[k][1], cs[k][2], cs[k][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(cs[k][4], cs[k][5], cs[k][6], cs[k][7]);
+      }
     }
   } else if (warp == 10) {
     // =============================== MMA issuer =========================================================
@@ -439,7 +470,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     const bool ld_on = !(a.ablate & 1);
     // software pipeline across tiles: the indices of the NEXT tile are read during the current one and its table rows pulled
     // into L2 (prefetch, no registers); the register loads are issued one MMA step ahead of their use
-    auto prefetch_l2 = [&](const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); };
     int64_t si = 0, ri = 0;
     if (my_tiles > 0) {
       const int64_t g0 = tile_row(0);
@@ -454,8 +484,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       const int64_t ri_cur = ri;
       const int64_t gnext = tile_row(t + 1);
       const bool vnext = t + 1 < my_tiles && gnext < rows;
-      int32_t si_n = 0, ri_n = 0;
-      if (vnext) { si_n = __ldg(a.senders + gnext); ri_n = __ldg(a.receivers + gnext); }   // consumed after E2
       const bool has_do = valid && a.grad_out != nullptr && ld_on, has_ga = valid && a.grad_agg != nullptr && ld_on;
       const __nv_bfloat16* dorow = a.grad_out + grow * kD + hh * 64;
       const __nv_bfloat16* garow = a.grad_agg + ri_cur * kD + hh * 64;
@@ -465,8 +493,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 64; ++j) pq[j] = 0u;
         if (ld_on) load_tables(si, ri, pq);
-        if (has_do) prefetch_l2(dorow);
-        if (has_ga) prefetch_l2(garow);
         if (t > 0) wait_cs(1, t - 1);                           // the producers' dH2' column sum has left this buffer
         wait_acc(100); if (tid == 0) stamp(a, t, 10);
         uint32_t h[32];
@@ -486,6 +512,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
         store_row(A, h);
         if (tid == 0) stamp(a, t, 11);
+        if (lane == 0) stamp(a, t, 32 + warp);
         done(-1);
       }
       // dO = grad_out[row] + grad_agg[receiver]: requested two phases before its first use
@@ -502,6 +529,10 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
           for (int k = 0; k < 4; ++k) ldg256_l1(garow + 16 * k, dq + 32 + 8 * k);
         }
+        // one rounding to bf16, the value every later use sees.  Consumed here, before the phase's proxy fence: a fence
+        // with global loads still in flight waits for them
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dreg[j] = add_bf16x2(dq[j], dq[32 + j]);
         // ---- E1: H2 = relu(H1 W1^T + b1) -> B -------------------------------------------------------------------
         if (t > 0) wait_cs(2, t - 1);                           // previous tile's dH1' column sum has left this buffer
         wait_acc(101); if (tid == 0) stamp(a, t, 12);
@@ -522,9 +553,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         store_row(B, h);
         if (tid == 0) stamp(a, t, 13);
         done(-1);
-        // the gradient rows have landed by now: one rounding to bf16, the value every later use sees
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dreg[j] = add_bf16x2(dq[j], dq[32 + j]);
       }
       // ---- E2: y = H2 W2^T + b2 ; LayerNorm forward statistics and backward -> dY -> C --------------------------------
       uint32_t preg[32];                                        // dO * yhat (bf16): gamma-gradient terms, summed after the phase
@@ -600,9 +628,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           cgamma[cg] += warp_colsum32(p, lane);
         }
       }
-      // indices of the next tile (their table rows are requested one phase later)
-      si = si_n; ri = ri_n;
-      if (vnext && ld_on) { prefetch_l2(a.proj_s + si * kD + hh * 64); prefetch_l2(a.proj_r + ri * kD + hh * 64); }
       // ---- E3: dH2' = (dY W2) * [H2 > 0] -> B ---------------------------------------------------------------------
       {
         wait_acc(103); if (tid == 0) stamp(a, t, 16);
@@ -636,7 +661,8 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         wait_cs(0, t);                                          // the producers' dY column sum has left buffer C
         wait_acc(104); if (tid == 0) stamp(a, t, 18);
         uint32_t hw[32], o[32];
-        load_row(A, hw);                                        // H1 (its buffer is refilled only after this phase)
+        load_row(A, hw);                                        // H1: the last reader of buffer A in this tile
+        mbar_arrive(&bars[kEbAfree]);
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
@@ -648,7 +674,11 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
         store_row(C, o);
         if (tid == 0) stamp(a, t, 19);
+        if (lane == 0) stamp(a, t, 40 + warp);
         done(2);
+        // indices of the next tile's row (an L2 hit: the producers touched them a tile ago); first used by the next E0
+        si = 0; ri = 0;
+        if (vnext) { si = __ldg(a.senders + gnext); ri = __ldg(a.receivers + gnext); }
         if (valid && !(a.ablate & 2)) {
           __nv_bfloat16* g0row = a.grad_pre0 + grow * kD + hh * 64;
 #pragma unroll
@@ -659,20 +689,27 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       {
         wait_acc(105); if (tid == 0) stamp(a, t, 20);
         __nv_bfloat16* derow = a.grad_edge + (valid ? grow : 0) * kD + hh * 64;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(acc, v0);
+        tmem_ld32(acc + 32, v1);
+        tmem_ld_wait();
+        // the accumulator is in registers: the next tile's step 0 may overwrite it while this phase does its arithmetic and
+        // stores (no shared-memory writes here, so no proxy fence)
+        fence_before_sync();
+        mbar_arrive(&bars[kEbEpi]);
+        uint32_t o[32];
 #pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32], o[16];
-          tmem_ld32(acc + cg * 32, v);
-          tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) {
+          const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1])), unpack_bf16x2(dreg[j]));
+          const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1])), unpack_bf16x2(dreg[16 + j]));
+          o[j] = pack_bf16(x0.x, x0.y);
+          o[16 + j] = pack_bf16(x1.x, x1.y);
+        }
+        if (valid && !(a.ablate & 2)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 x = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), unpack_bf16x2(dreg[cg * 16 + j]));
-            o[j] = pack_bf16(x.x, x.y);
-          }
-          if (valid && !(a.ablate & 2)) { stg256(derow + cg * 32, o); stg256(derow + cg * 32 + 16, o + 8); }
+          for (int k = 0; k < 4; ++k) stg256(derow + 16 * k, o + 8 * k);
         }
         if (tid == 0) stamp(a, t, 21);
-        done(-1);
       }
     }
     // ---- drain the weight-gradient accumulators and the LayerNorm vector partials ---------------------------------------
@@ -860,8 +897,8 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
   { const char* ab = getenv("HGN_TC_ABLATE"); a.ablate = ab ? atoi(ab) : 0; }
   static long long* tl_dev = nullptr;
   if (a.ablate & 64) {
-    if (tl_dev == nullptr) cudaMalloc(&tl_dev, 8 * 32 * sizeof(long long));
-    cudaMemsetAsync(tl_dev, 0, 8 * 32 * sizeof(long long), st);
+    if (tl_dev == nullptr) cudaMalloc(&tl_dev, 8 * 48 * sizeof(long long));
+    cudaMemsetAsync(tl_dev, 0, 8 * 48 * sizeof(long long), st);
     a.timeline = tl_dev;
   }
   const int64_t tiles = ceil_div(num_edges, kTile);
@@ -871,12 +908,12 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
   }
   HGN_LAUNCH_OK("edge_bwd_tc");
   if (a.timeline != nullptr) {
-    long long h[8 * 32];
+    long long h[8 * 48];
     cudaMemcpyAsync(h, a.timeline, sizeof(h), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     for (int t = 0; t < 8; ++t) {
       fprintf(stderr, "tile %d:", t);
-      for (int k = 0; k < 30; ++k) fprintf(stderr, " %lld", h[t * 32 + k] ? h[t * 32 + k] - h[0] : -1);
+      for (int k = 0; k < 48; ++k) fprintf(stderr, " %lld", h[t * 48 + k] ? h[t * 48 + k] - h[0] : -1);
       fprintf(stderr, "\n");
     }
   }
