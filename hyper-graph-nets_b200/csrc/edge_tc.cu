@@ -28,58 +28,6 @@
 
 namespace hgn {
 
-__device__ __forceinline__ void st_shared128(uint32_t addr, const uint32_t* w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_shared32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void ld_shared128(uint32_t addr, uint32_t* w) {
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
-}
-// packed bf16 helpers (one SASS instruction each: F2FP.RELU.BF16.F32.PACK_AB, HFMA2.BF16_V2, HSET2 + HMUL2)
-__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ uint32_t add_bf16x2(uint32_t x, uint32_t y) {
-  uint32_t d;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(y));
-  return d;
-}
-// g * [h > 0] per 16-bit half: ReLU backward against the stored activation
-__device__ __forceinline__ uint32_t relu_bwd_bf16x2(uint32_t g, uint32_t h) {
-  uint32_t d;
-  asm("{\n\t.reg .b32 m;\n\tset.gt.bf16x2.bf16x2 m, %2, %3;\n\tmul.rn.bf16x2 %0, %1, m;\n\t}" : "=r"(d) : "r"(g), "r"(h), "r"(0u));
-  return d;
-}
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
-// 256-bit read-only load that allocates in L1: gathered table rows are shared by neighbouring edges of a tile
-__device__ __forceinline__ void ldg256_l1(const void* p, uint32_t* v) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
-}
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// Column sums over the 32 lanes of a warp: x[j] is this lane's (= this row's) value in column j.  Returns, in lane j,
-// the sum over all 32 lanes of column j (recursive halving: 31 shuffles).  Fixed association order.
-__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? x[i] : x[i + off];
-      const float keep = up ? x[i + off] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return x[0];
-}
-
 // =========================================================================================================
 // node projection and its data gradient:  out_o[rows,128] = sum_c in_c[rows,128] * B(chunk chunk0 + o + c)
 //   forward (b_mn = 0): n_in = 1, n_out = 2:  Ps = v Ws^T, Pr = v Wr^T          (B K-major:  out[n] = sum_k in[k] W[n][k])
@@ -842,8 +790,13 @@ int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packe
   return HGN_OK;
 }
 
+int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
+                       const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st);   // edge_fwd_tc.cu
+
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
                            const int32_t* receivers, const void* packed, void* out, cudaStream_t st) {
+  static const bool legacy = getenv("HGN_EDGE_FWD_LEGACY") != nullptr;     // development: the generic tile kernel with a pre-add
+  if (!legacy) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, "edge_fwd_tc", st);
   hgn_chunks ch{};
   ch.n_chunks = 1;
   ch.src[0] = edge;
@@ -854,7 +807,7 @@ int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj
   pre.receivers = receivers;
   pre.w0_chunks = 3;
   pre.w0_chunk0 = 2;
-  return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc", st);
+  return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc_legacy", st);
 }
 
 struct EdgeBwdLayout { size_t w_partial, epi, prod, total; int grid; };

@@ -38,6 +38,60 @@ __device__ __forceinline__ void load_weight_block(uint32_t smem_dst, const __nv_
   }
 }
 
+// ---- epilogue helpers shared by the projected edge kernels ----------------------------------------------------
+__device__ __forceinline__ void st_shared128(uint32_t addr, const uint32_t* w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ld_shared128(uint32_t addr, uint32_t* w) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
+}
+// packed bf16 helpers (one SASS instruction each: F2FP.RELU.BF16.F32.PACK_AB, HFMA2.BF16_V2, HSET2 + HMUL2)
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t x, uint32_t y) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(y));
+  return d;
+}
+// g * [h > 0] per 16-bit half: ReLU backward against the stored activation
+__device__ __forceinline__ uint32_t relu_bwd_bf16x2(uint32_t g, uint32_t h) {
+  uint32_t d;
+  asm("{\n\t.reg .b32 m;\n\tset.gt.bf16x2.bf16x2 m, %2, %3;\n\tmul.rn.bf16x2 %0, %1, m;\n\t}" : "=r"(d) : "r"(g), "r"(h), "r"(0u));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+// 256-bit read-only load that allocates in L1: gathered table rows are shared by neighbouring edges of a tile
+__device__ __forceinline__ void ldg256_l1(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Column sums over the 32 lanes of a warp: x[j] is this lane's (= this row's) value in column j.  Returns, in lane j,
+// the sum over all 32 lanes of column j (recursive halving: 31 shuffles).  Fixed association order.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+
+
 // Optional "projected" first layer (edge update): layer 0 consumes only the chunks listed in `ch` (the edge rows) with the
 // W0 column block starting at chunk `w0_chunk0` of a `w0_chunks`-wide packed W0, and the epilogue adds the per-node
 // pre-projections  proj_s[senders[row]] + proj_r[receivers[row]]  (= v[s] W0[:,0:128]^T + v[r] W0[:,128:256]^T computed once
