@@ -4,7 +4,7 @@
 // (graphnet.py:34-48) with e := v, Ps := agg Wagg^T gathered through the identity (senders == nullptr) and no Pr.
 //
 // Persistent, one CTA per SM, two 128-row tiles in flight:
-//   warp 17     TMA thread: cp.async.bulk.tensor loads of the [128 x 128] bf16 edge tile (two 128B-swizzled panels) into a
+//   warp 17     loader (lane 0 = TMA thread; all lanes: gather indices -> shared-memory ring, table rows -> L2 prefetch): cp.async.bulk.tensor loads of the [128 x 128] bf16 edge tile (two 128B-swizzled panels) into a
 //               3-stage ring; after the epilogue has turned a stage into the OUTPUT tile in place (residual add), the same
 //               thread stores it with cp.async.bulk.tensor and recycles the stage once the store has read it
 //   warp 16     MMA issuer: per tile  GEMM0 = e We^T (A from the stage, SS), GEMM1 = H1 W1^T, GEMM2 = H2 W2^T (A = bf16
@@ -24,14 +24,16 @@
 namespace hgn {
 
 constexpr int kEfSetThreads = 256;
-constexpr int kEfThreads = 2 * kEfSetThreads + 64;     // 18 warps
+constexpr int kEfThreads = 2 * kEfSetThreads + 64;     // 18 warps (17-20 warps: at most 96 registers per thread)
 constexpr int kEfStages = 3;
 constexpr uint32_t kEfWe = 0, kEfW1 = kChunkBytes, kEfW2 = 2 * kChunkBytes, kEfStage = 3 * kChunkBytes;
 constexpr uint32_t kEfParams = kEfStage + kEfStages * kChunkBytes;     // b0 b1 b2 gamma beta (fp32 x 128 each)
 constexpr uint32_t kEfXch = kEfParams + 5 * kD * 4;                    // float2 [set][tile parity][half][128]
-constexpr uint32_t kEfBars = kEfXch + 2 * 2 * 2 * kTile * 8;
+constexpr int kEfRing = 8;                             // tiles of gather indices kept in shared memory (> lookahead + tiles in flight)
+constexpr uint32_t kEfIdx = kEfXch + 2 * 2 * 2 * kTile * 8;              // int32 [ring][2][128]: table row of every tile row
+constexpr uint32_t kEfBars = kEfIdx + kEfRing * 2 * kTile * 4;
 constexpr uint32_t kEfSmem = kEfBars + 128;
-enum { kEfFull = 0, kEfAcc = 3, kEfEpi = 5, kEfOut = 7, kEfTmem = 9 };
+enum { kEfFull = 0, kEfOut = 3, kEfAcc = 6, kEfEpi = 8, kEfTmem = 10, kEfIdxDone = 12 };
 
 struct EdgeFwdArgs {
   const __nv_bfloat16 *proj_s, *proj_r;     // per-node tables; proj_r may be null
@@ -60,6 +62,7 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     if (tid == 0) {
       for (int s = 0; s < kEfStages; ++s) mbar_init(&bars[kEfFull + s], 1);
       for (int s = 0; s < 2; ++s) { mbar_init(&bars[kEfAcc + s], 1); mbar_init(&bars[kEfEpi + s], kEfSetThreads); mbar_init(&bars[kEfOut + s], kEfSetThreads); }
+      *reinterpret_cast<volatile int*>(&bars[kEfIdxDone]) = 0;
       mbar_init_fence();
     }
     if (warp == 16) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[kEfTmem]));
@@ -76,12 +79,29 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
   auto tile_row0 = [&](int64_t it) -> int64_t { return (blockIdx.x + it * gridDim.x) * kTile; };
 
   if (warp == 17) {
-    // =============================== TMA thread =========================================================
-    if (lane == 0) {
-      for (int64_t i = 0; i < my_tiles + kEfStages; ++i) {
-        if (i >= kEfStages) {                     // tile j sits finished in the stage tile i wants: store it, then reuse
-          const int64_t j = i - kEfStages;
-          mbar_wait(&bars[kEfOut + int(j & 1)], uint32_t(j >> 1) & 1, 30);
+    // =============================== loader warp ==========================================================
+    // Per tile: (lane 0) TMA load of the edge tile into its ring stage as soon as the stage is free; (all lanes) the tile's
+    // gather indices, read one tile ahead, are published in a shared-memory ring for the epilogue threads (an index held in
+    // a register across a tile gets spilled, and the spill store waits for the load) and the table rows they name are
+    // pulled into L2 with fire-and-forget prefetches, two to three tiles before the epilogue gathers them.
+    auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); };
+    int32_t* ring = reinterpret_cast<int32_t*>(smem + kEfIdx);
+    int32_t cs[4], cr[4], ns[4], nr[4];
+    auto fetch = [&](int64_t i, int32_t (&s4)[4], int32_t (&r4)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t grow = tile_row0(i) + lane + 32 * j;
+        const bool ok = i < my_tiles && grow < rows;
+        s4[j] = ok ? (a.senders != nullptr ? __ldg(a.senders + grow) : int32_t(grow)) : 0;
+        r4[j] = ok ? (a.receivers != nullptr ? __ldg(a.receivers + grow) : int32_t(grow)) : 0;
+      }
+    };
+    fetch(0, cs, cr);
+    for (int64_t i = 0; i < my_tiles + kEfStages; ++i) {
+      if (i >= kEfStages) {                       // tile j sits finished in the stage tile i wants: store it, then reuse
+        const int64_t j = i - kEfStages;
+        mbar_wait(&bars[kEfOut + int(j & 1)], uint32_t(j >> 1) & 1, 30);
+        if (lane == 0) {
           const uint32_t src = stage_addr(j);
           const int y = int(tile_row0(j));
           tma_store_2d(&tm_out, src, 0, y);
@@ -89,17 +109,35 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           tma_store_commit();
           tma_store_wait_read<0>();
         }
-        if (i < my_tiles) {
-          uint64_t* full = &bars[kEfFull + int(i % kEfStages)];
-          const uint32_t dst = stage_addr(i);
-          const int y = int(tile_row0(i));
-          mbar_expect_tx(full, kChunkBytes);
-          tma_load_2d(dst, &tm_in, 0, y, full);
-          tma_load_2d(dst + kPanel, &tm_in, 64, y, full);
-        }
+        __syncwarp();
       }
-      tma_store_wait<0>();
+      if (i >= my_tiles) continue;
+      if (lane == 0) {
+        const int st = int(i % kEfStages);
+        const uint32_t dst = stage_addr(i);
+        const int y = int(tile_row0(i));
+        mbar_expect_tx(&bars[kEfFull + st], kChunkBytes);
+        tma_load_2d(dst, &tm_in, 0, y, &bars[kEfFull + st]);
+        tma_load_2d(dst + kPanel, &tm_in, 64, y, &bars[kEfFull + st]);
+      }
+      fetch(i + 1, ns, nr);
+      int32_t* slot = ring + int(i % kEfRing) * 2 * kTile;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        slot[lane + 32 * j] = cs[j];
+        slot[kTile + lane + 32 * j] = cr[j];
+        pf(a.proj_s + int64_t(cs[j]) * kD); pf(a.proj_s + int64_t(cs[j]) * kD + 64);
+        if (a.proj_r != nullptr) { pf(a.proj_r + int64_t(cr[j]) * kD); pf(a.proj_r + int64_t(cr[j]) * kD + 64); }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&bars[kEfIdxDone]) = int(i + 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cs[j] = ns[j]; cr[j] = nr[j]; }
     }
+    if (lane == 0) tma_store_wait<0>();
   } else if (warp == 16) {
     // =============================== MMA issuer =========================================================
     if (lane == 0) {
@@ -151,17 +189,16 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       mbar_wait(&bars[kEfAcc + set], acc_phase++ & 1, tag);
       fence_after_sync();
     };
-    auto row_index = [&](const int32_t* idx, int64_t grow) -> int64_t { return idx != nullptr ? int64_t(__ldg(idx + grow)) : grow; };
-    int64_t si = 0, ri = 0;
-    if (set < my_tiles) {
-      const int64_t g0 = tile_row0(set) + r;
-      if (g0 < rows) { si = row_index(a.senders, g0); ri = row_index(a.receivers, g0); }
-    }
+    const int32_t* ring = reinterpret_cast<const int32_t*>(smem + kEfIdx);
     for (int64_t it = set; it < my_tiles; it += 2) {
       // table rows of this tile, in four blocks of 16 columns: two blocks are requested before the accumulator wait, the other
-      // two while the first ones are consumed (64 table registers at once would spill); and the indices of this set's next tile
-      const __nv_bfloat16* psrow = a.proj_s + si * kD + hh * 64;
-      const __nv_bfloat16* prrow = a.proj_r != nullptr ? a.proj_r + ri * kD + hh * 64 : nullptr;
+      // two while the first ones are consumed (64 table registers at once would spill); the row indices come from the prefetch warp's ring
+      for (uint32_t spin = 0; *reinterpret_cast<volatile int*>(&bars[kEfIdxDone]) <= int(it); ++spin)
+        if (spin > (1u << 26)) { debug_record(35, uint32_t(it), 0, 0, 0, 0, 0); __trap(); }
+      __threadfence_block();
+      const int32_t* slot = ring + int(it % kEfRing) * 2 * kTile;
+      const __nv_bfloat16* psrow = a.proj_s + int64_t(slot[r]) * kD + hh * 64;
+      const __nv_bfloat16* prrow = a.proj_r != nullptr ? a.proj_r + int64_t(slot[kTile + r]) * kD + hh * 64 : nullptr;
       uint32_t pa[2][8], pb[2][8];              // Ps / Pr words of the blocks in flight (ring of two)
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -171,11 +208,6 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) pb[k][j] = 0u;
         }
-      }
-      {
-        const int64_t gnext = tile_row0(it + 2) + r;
-        si = 0; ri = 0;
-        if (it + 2 < my_tiles && gnext < rows) { si = row_index(a.senders, gnext); ri = row_index(a.receivers, gnext); }
       }
       // ---- P0: H1 = relu(e We^T + Ps[s] + Pr[r] + b0) -> TMEM ------------------------------------------------
       wait_acc(100);

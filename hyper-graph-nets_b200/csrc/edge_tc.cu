@@ -409,16 +409,16 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       for (int k = 0; k < 8; ++k) ld_shared128(bufaddr + row_off + sw128_chunk(r, k), w + 4 * k);
     };
     auto tile_row = [&](int64_t tt) { return (blockIdx.x + tt * gridDim.x) * kTile + r; };
-    auto load_tables = [&](int64_t si, int64_t ri, uint32_t* pq) {          // Ps[s] and Pr[r]: my 64 columns of each
-      const __nv_bfloat16* psrow = a.proj_s + si * kD + hh * 64;
-      const __nv_bfloat16* prrow = a.proj_r + ri * kD + hh * 64;
+    auto load_tables = [&](int32_t si, int32_t ri, uint32_t* pq) {          // Ps[s] and Pr[r]: my 64 columns of each
+      const __nv_bfloat16* psrow = a.proj_s + int64_t(si) * kD + hh * 64;
+      const __nv_bfloat16* prrow = a.proj_r + int64_t(ri) * kD + hh * 64;
 #pragma unroll
       for (int k = 0; k < 4; ++k) { ldg256_l1(psrow + 16 * k, pq + 8 * k); ldg256_l1(prrow + 16 * k, pq + 32 + 8 * k); }
     };
     const bool ld_on = !(a.ablate & 1);
     // software pipeline across tiles: the indices of the NEXT tile are read during the current one and its table rows pulled
     // into L2 (prefetch, no registers); the register loads are issued one MMA step ahead of their use
-    int64_t si = 0, ri = 0;
+    int32_t si = 0, ri = 0;                                   // 32-bit until used: widening at the load would wait for it
     if (my_tiles > 0) {
       const int64_t g0 = tile_row(0);
       if (g0 < rows) { si = __ldg(a.senders + g0); ri = __ldg(a.receivers + g0); }
