@@ -96,6 +96,12 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
                             void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
                             float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, cudaStream_t st);
+size_t node_update_backward_workspace_tc(int64_t num_nodes);
+int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed, const void* grad_out,
+                            void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
+                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 static int check_chunks(const hgn_chunks* ch, const char* who) {
   HGN_CHECK_ARG(ch != nullptr, "%s: chunks is NULL", who);
   HGN_CHECK_ARG(ch->n_chunks >= 1 && ch->n_chunks <= HGN_MAX_CHUNKS, "%s: n_chunks=%d outside [1,%d]", who, ch->n_chunks, HGN_MAX_CHUNKS);
@@ -234,6 +240,32 @@ extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void
   return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, grad_out, grad_agg, grad_edge, grad_pre0,
                                  grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes,
                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out,
+                                       void* stream) {
+  HGN_BF16_ONLY("node_update_forward");
+  HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "node_update_forward: num_nodes=%lld", (long long)num_nodes);
+  if (num_nodes == 0) return HGN_OK;
+  HGN_CHECK_ARG(v && agg && packed && q && out, "node_update_forward: null pointer");
+  return node_update_forward_tc(num_nodes, v, agg, packed, q, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes) {
+  if (dtype != HGN_BF16 || num_nodes < 0) return 0;
+  return node_update_backward_workspace_tc(num_nodes);
+}
+
+extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed,
+                                        const void* grad_out, void* grad_v, void* grad_agg, float* grad_W0, float* grad_b0, float* grad_W1,
+                                        float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  HGN_BF16_ONLY("node_update_backward");
+  HGN_CHECK_ARG(num_nodes > 0 && num_nodes < (int64_t(1) << 31), "node_update_backward: num_nodes=%lld", (long long)num_nodes);
+  HGN_CHECK_ARG(v && agg && q && packed && grad_out && grad_v && grad_agg && workspace, "node_update_backward: null pointer");
+  HGN_CHECK_ARG(grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta, "node_update_backward: null pointer");
+  return node_update_backward_tc(num_nodes, v, agg, q, packed, grad_out, grad_v, grad_agg, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
+                                 grad_gamma, grad_beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hgn_profile_enable(int on) { g_profile_on = on != 0; return HGN_OK; }

@@ -55,7 +55,8 @@ proj_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ pack
   const PackedTc P(la.w0_chunks);
   {
     const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + la.chunk0 * kD;
-    for (int c = 0; c < 2; ++c) load_weight_block(sbase + w_off + c * kChunkBytes, w0g + c * kD, int64_t(la.w0_chunks) * kD, tid, kLinThreads);
+    const int n_w = la.n_in > la.n_out ? la.n_in : la.n_out;
+    for (int c = 0; c < n_w; ++c) load_weight_block(sbase + w_off + c * kChunkBytes, w0g + c * kD, int64_t(la.w0_chunks) * kD, tid, kLinThreads);
     cp_async_commit();
     if (tid == 0) {
       for (int s = 0; s < 2; ++s) {
@@ -182,6 +183,7 @@ struct EdgeBwdArgs {
   float* epi_colpart;               // [grid][4][2][128]    beta, gamma partial column sums per lane quadrant
   float* prod_colpart;              // [grid][3][128]       db2, db1, db0
   long long* timeline;              // development: clock64 stamps of block 0 ([tile][32]) when HGN_TC_ABLATE has bit 64
+  int w0_chunks, w0_chunk0;         // W0 is [128][128 w0_chunks]; the dense input multiplies chunk w0_chunk0
   int ablate;                       // development switches (HGN_TC_ABLATE): 1 no table/gradient loads, 2 no HBM stores,
                                     // 4 no LayerNorm-vector column sums, 8 no bias column sums, 16 no weight-gradient MMAs
 };
@@ -197,13 +199,13 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
   if ((sbase & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEbBars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const PackedTc P(3);
+  const PackedTc P(a.w0_chunks);
   float* prm = reinterpret_cast<float*>(smem + kEbParams);
   {
     const float* pg = reinterpret_cast<const float*>(packed + P.params);
     for (int i = tid; i < 5 * kD; i += kEbThreads) prm[i] = pg[i];
     const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
-    load_weight_block(sbase + kEbWe, w0g + 2 * kD, 3 * kD, tid, kEbThreads);
+    load_weight_block(sbase + kEbWe, w0g + a.w0_chunk0 * kD, int64_t(a.w0_chunks) * kD, tid, kEbThreads);
     load_weight_block(sbase + kEbW1, reinterpret_cast<const __nv_bfloat16*>(packed + P.w1), kD, tid, kEbThreads);
     load_weight_block(sbase + kEbW2, reinterpret_cast<const __nv_bfloat16*>(packed + P.w2), kD, tid, kEbThreads);
     cp_async_commit();
@@ -286,11 +288,12 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         for (int j = 0; j < 2; ++j) {
           const int64_t grow = row0 + ptid + 64 * j;
           if (grow < rows) {
-            const int64_t si = __ldg(a.senders + grow), ri = __ldg(a.receivers + grow);
+            const int64_t si = a.senders != nullptr ? int64_t(__ldg(a.senders + grow)) : grow;
+            const int64_t ri = a.receivers != nullptr ? int64_t(__ldg(a.receivers + grow)) : grow;
             pf(a.edge + grow * kD); pf(a.edge + grow * kD + 64);
             if (a.grad_out != nullptr) { pf(a.grad_out + grow * kD); pf(a.grad_out + grow * kD + 64); }
             pf(a.proj_s + si * kD); pf(a.proj_s + si * kD + 64);
-            pf(a.proj_r + ri * kD); pf(a.proj_r + ri * kD + 64);
+            if (a.proj_r != nullptr) { pf(a.proj_r + ri * kD); pf(a.proj_r + ri * kD + 64); }
             if (a.grad_agg != nullptr) { pf(a.grad_agg + ri * kD); pf(a.grad_agg + ri * kD + 64); }
           }
         }
@@ -411,17 +414,22 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     auto tile_row = [&](int64_t tt) { return (blockIdx.x + tt * gridDim.x) * kTile + r; };
     auto load_tables = [&](int32_t si, int32_t ri, uint32_t* pq) {          // Ps[s] and Pr[r]: my 64 columns of each
       const __nv_bfloat16* psrow = a.proj_s + int64_t(si) * kD + hh * 64;
-      const __nv_bfloat16* prrow = a.proj_r + int64_t(ri) * kD + hh * 64;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { ldg256_l1(psrow + 16 * k, pq + 8 * k); ldg256_l1(prrow + 16 * k, pq + 32 + 8 * k); }
+      for (int k = 0; k < 4; ++k) ldg256_l1(psrow + 16 * k, pq + 8 * k);
+      if (a.proj_r != nullptr) {
+        const __nv_bfloat16* prrow = a.proj_r + int64_t(ri) * kD + hh * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ldg256_l1(prrow + 16 * k, pq + 32 + 8 * k);
+      }
     };
     const bool ld_on = !(a.ablate & 1);
     // software pipeline across tiles: the indices of the NEXT tile are read during the current one and its table rows pulled
     // into L2 (prefetch, no registers); the register loads are issued one MMA step ahead of their use
+    auto row_index = [&](const int32_t* idx, int64_t grow) -> int32_t { return idx != nullptr ? __ldg(idx + grow) : int32_t(grow); };
     int32_t si = 0, ri = 0;                                   // 32-bit until used: widening at the load would wait for it
     if (my_tiles > 0) {
       const int64_t g0 = tile_row(0);
-      if (g0 < rows) { si = __ldg(a.senders + g0); ri = __ldg(a.receivers + g0); }
+      if (g0 < rows) { si = row_index(a.senders, g0); ri = row_index(a.receivers, g0); }
     }
     for (int64_t t = 0; t < my_tiles; ++t) {
       const uint32_t A = buf(1, t), B = buf(2, t), C = buf(3, t);
@@ -626,7 +634,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         done(2);
         // indices of the next tile's row (an L2 hit: the producers touched them a tile ago); first used by the next E0
         si = 0; ri = 0;
-        if (vnext) { si = __ldg(a.senders + gnext); ri = __ldg(a.receivers + gnext); }
+        if (vnext) { si = row_index(a.senders, gnext); ri = row_index(a.receivers, gnext); }
         if (valid && !(a.ablate & 2)) {
           __nv_bfloat16* g0row = a.grad_pre0 + grow * kD + hh * 64;
 #pragma unroll
@@ -696,14 +704,14 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 
 // fixed-order reduction of the per-CTA partials of edge_bwd_tc_kernel
 __global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, const float* __restrict__ epi_colpart,
-                                       const float* __restrict__ prod_colpart, int parts, float* __restrict__ gW0, float* __restrict__ gW1,
+                                       const float* __restrict__ prod_colpart, int parts, int w0_chunks, int w0_chunk0, float* __restrict__ gW0, float* __restrict__ gW1,
                                        float* __restrict__ gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * kD * kD) {
     float s = 0.f;
     for (int p = 0; p < parts; ++p) s += w_partial[int64_t(p) * 3 * kD * kD + i];
     const int z = i / (kD * kD), o = (i / kD) % kD, c = i % kD;
-    if (z == 0) gW0[int64_t(o) * 3 * kD + 2 * kD + c] = s;
+    if (z == 0) gW0[(int64_t(o) * w0_chunks + w0_chunk0) * kD + c] = s;
     else if (z == 1) gW1[o * kD + c] = s;
     else gW2[o * kD + c] = s;
   } else if (i < 3 * kD * kD + 5 * kD) {
@@ -826,27 +834,30 @@ static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
 
 size_t edge_update_backward_workspace_tc(int64_t num_edges) { return edge_bwd_layout(num_edges).total; }
 
-int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
-                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
-                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  const EdgeBwdLayout L = edge_bwd_layout(num_edges);
-  if (workspace_bytes < L.total) { set_error("edge_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+// Backward of  out = dense + LN(MLP(We dense + Ps[s] + Pr[r] + b0 ...)):  grad_dense, grad_pre0 (= G0) and every weight gradient
+// except the W0 blocks that multiply the node tables (those follow from G0 at node level).  gW0's block w0_chunk0 is written.
+static int projected_backward_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders,
+                                     const int32_t* receivers, const void* packed, int w0_chunks, int w0_chunk0, const void* grad_out,
+                                     const void* grad_agg, void* grad_dense, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1,
+                                     float* gW2, float* gb2, float* ggamma, float* gbeta, void* workspace, const char* name, cudaStream_t st) {
+  const EdgeBwdLayout L = edge_bwd_layout(rows);
   if (int rc = configure_edge_kernels()) return rc;
   char* ws = static_cast<char*>(workspace);
   EdgeBwdArgs a{};
-  a.edge = static_cast<const __nv_bfloat16*>(edge);
+  a.edge = static_cast<const __nv_bfloat16*>(dense);
   a.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
   a.proj_r = static_cast<const __nv_bfloat16*>(proj_r);
   a.senders = senders;
   a.receivers = receivers;
   a.grad_out = static_cast<const __nv_bfloat16*>(grad_out);
   a.grad_agg = static_cast<const __nv_bfloat16*>(grad_agg);
-  a.grad_edge = static_cast<__nv_bfloat16*>(grad_edge);
+  a.grad_edge = static_cast<__nv_bfloat16*>(grad_dense);
   a.grad_pre0 = static_cast<__nv_bfloat16*>(grad_pre0);
   a.w_partial = reinterpret_cast<float*>(ws + L.w_partial);
   a.epi_colpart = reinterpret_cast<float*>(ws + L.epi);
   a.prod_colpart = reinterpret_cast<float*>(ws + L.prod);
+  a.w0_chunks = w0_chunks;
+  a.w0_chunk0 = w0_chunk0;
   { const char* ab = getenv("HGN_TC_ABLATE"); a.ablate = ab ? atoi(ab) : 0; }
   static long long* tl_dev = nullptr;
   if (a.ablate & 64) {
@@ -854,12 +865,12 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
     cudaMemsetAsync(tl_dev, 0, 8 * 48 * sizeof(long long), st);
     a.timeline = tl_dev;
   }
-  const int64_t tiles = ceil_div(num_edges, kTile);
+  const int64_t tiles = ceil_div(rows, kTile);
   {
-    HGN_TIMED("edge_bwd_tc", st);
-    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(num_edges, tiles, static_cast<const uint8_t*>(packed), a);
+    HGN_TIMED(name, st);
+    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a);
   }
-  HGN_LAUNCH_OK("edge_bwd_tc");
+  HGN_LAUNCH_OK(name);
   if (a.timeline != nullptr) {
     long long h[8 * 48];
     cudaMemcpyAsync(h, a.timeline, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -872,10 +883,70 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
   }
   {
     HGN_TIMED("reduce_weight_partials", st);
-    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, gW0, gW1, gW2,
-                                                                              gb0, gb1, gb2, ggamma, gbeta);
+    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, a.w0_chunks, a.w0_chunk0,
+                                                                              gW0, gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
   }
   HGN_LAUNCH_OK("edge_bwd_reduce");
+  return HGN_OK;
+}
+
+int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
+                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
+                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
+                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const EdgeBwdLayout L = edge_bwd_layout(num_edges);
+  if (workspace_bytes < L.total) { set_error("edge_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  return projected_backward_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, grad_out, grad_agg, grad_edge, grad_pre0,
+                                   gW0, gb0, gW1, gb1, gW2, gb2, ggamma, gbeta, workspace, "edge_bwd_tc", st);
+}
+
+// ---- node update in 'sum' mode through the same kernels (graphnet.py:34-48 with one aggregate) ---------------------------
+//   v' = v + LN(MLP([v | agg]))  with  W0 = [Wv | Wa]:  pre0 = Wv v + Q + b0,  Q = agg Wa^T  (one projection per node row, gathered
+//   through the identity), so the fused forward / backward kernels of the edge update serve the node update unchanged.
+int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, cudaStream_t st) {
+  LinArgs la{};
+  la.in[0] = static_cast<const __nv_bfloat16*>(agg);
+  la.out[0] = static_cast<__nv_bfloat16*>(q);
+  la.n_in = 1; la.n_out = 1; la.b_mn = 0; la.w0_chunks = 2; la.chunk0 = 1;
+  if (int rc = launch_proj(num_nodes, packed, la, "node_project_fwd", st)) return rc;
+  return edge_fwd_tc_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, out, "node_fwd_tc", st);
+}
+
+struct NodeBwdLayout { size_t edge, g0, partial, total; int parts; };
+static NodeBwdLayout node_bwd_layout(int64_t n) {
+  NodeBwdLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.parts = tc_pair_wgrad_parts(n);
+  L.edge = take(edge_bwd_layout(n).total);
+  L.g0 = take(size_t(n > 0 ? n : 1) * kD * 2);
+  L.partial = take(size_t(L.parts) * 2 * kD * kD * 4);
+  L.total = off;
+  return L;
+}
+size_t node_update_backward_workspace_tc(int64_t num_nodes) { return node_bwd_layout(num_nodes).total; }
+
+int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed, const void* grad_out,
+                            void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
+                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const NodeBwdLayout L = node_bwd_layout(num_nodes);
+  if (workspace_bytes < L.total) { set_error("node_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  char* ws = static_cast<char*>(workspace);
+  void* g0 = ws + L.g0;
+  if (int rc = projected_backward_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1,
+                                         gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) return rc;
+  LinArgs la{};                                  // d agg = G0 Wa
+  la.in[0] = static_cast<const __nv_bfloat16*>(g0);
+  la.out[0] = static_cast<__nv_bfloat16*>(grad_agg);
+  la.n_in = 1; la.n_out = 1; la.b_mn = 1; la.w0_chunks = 2; la.chunk0 = 1;
+  if (int rc = launch_proj(num_nodes, packed, la, "node_project_dgrad", st)) return rc;
+  float* partial = reinterpret_cast<float*>(ws + L.partial);     // d Wa = G0^T agg
+  if (int rc = tc_pair_wgrad(num_nodes, g0, agg, nullptr, nullptr, partial, L.parts, st)) return rc;
+  {
+    HGN_TIMED("reduce_weight_partials", st);
+    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 1, gW0, 2 * kD, kD);
+  }
+  HGN_LAUNCH_OK("node_update_backward reductions");
   return HGN_OK;
 }
 

@@ -566,7 +566,8 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int part = blockIdx.x, group = blockIdx.y, nch = ch.n_chunks;
   const int c_first = group == 0 ? 0 : 3 * (group - 1);
-  const int n_out = group == 0 ? 2 : min(3, nch - c_first);          // accumulators of this CTA
+  const bool single = group == 0 && wa.G1 == nullptr;                // one (G, Z) pair only
+  const int n_out = group == 0 ? (single ? 1 : 2) : min(3, nch - c_first);   // accumulators of this CTA
   const int n_tiles = group == 0 ? 4 : 1 + n_out;                    // operand tiles per stage
   const int64_t row_end = min(rows, slab0 + slab_rows);
   const int64_t r_beg = slab0 + int64_t(part) * rows_per_part;
@@ -613,7 +614,7 @@ mlp_wgrad_tc_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int64_t rows
       const int64_t row0 = r_beg + st * kWgRows;
       const uint32_t saddr = sbase + stage * kWgStageBytes + (c16 >> 3) * 8192;
       // dense workspace tiles (slab-local rows)
-      const int n_dense = group == 0 ? 4 : 1;
+      const int n_dense = group == 0 ? (single ? 2 : 4) : 1;
       for (int t = 0; t < n_dense; ++t) {
         const __nv_bfloat16* src = group == 0 ? (t == 0 ? wa.G2 : t == 1 ? wa.H2 : t == 2 ? wa.G1 : wa.H1) : wa.G0;
 #pragma unroll

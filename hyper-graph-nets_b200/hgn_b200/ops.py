@@ -403,6 +403,59 @@ def edge_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Ten
     return _EdgeUpdate.apply(ps, pr, e, *params, packed, s_plan, r_plan, bool(want_agg))
 
 
+class _NodeUpdate(torch.autograd.Function):
+    """``v' = v + LN(MLP([v | agg]))`` (graphnet.py:34-48 with one 'sum' aggregate) on the projected kernels: the aggregate's
+    block of the first linear is applied once per node row (``q = agg Wa^T``) and enters the fused kernel as a table row."""
+
+    @staticmethod
+    def forward(ctx, v, agg, W0, b0, W1, b1, W2, b2, gamma, beta, packed):
+        lib = _cabi.load()
+        n = v.shape[0]
+        q = torch.empty_like(v)
+        out = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            _cabi.check(lib.hgn_node_update_forward(_cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), packed.data_ptr(), q.data_ptr(),
+                                                    out.data_ptr(), _cabi.stream_ptr()), "hgn_node_update_forward")
+        _count(2)
+        ctx.save_for_backward(v, agg, q)
+        ctx.packed = packed
+        ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _cabi.load()
+        v, agg, q = ctx.saved_tensors
+        n, dev = v.shape[0], v.device
+        grad_out = grad_out.contiguous().to(v.dtype)
+        grad_v = torch.empty_like(v)
+        grad_agg = torch.empty_like(agg)
+        gparams = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes]
+        with torch.cuda.device(dev):
+            ws_bytes = lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.hgn_node_update_backward(
+                _cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), q.data_ptr(), ctx.packed.data_ptr(), grad_out.data_ptr(),
+                grad_v.data_ptr(), grad_agg.data_ptr(), *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
+                "hgn_node_update_backward")
+        _count(5)
+        return (grad_v, grad_agg, *gparams, None)
+
+
+def node_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Tensor, agg: torch.Tensor) -> torch.Tensor:
+    """Projected bf16 node update with a single aggregate: ``v + LN(MLP([v | agg]))``."""
+    _cabi.require_cuda(v, agg)
+    if v.dtype != torch.bfloat16 or agg.dtype != torch.bfloat16:
+        raise _cabi.HgnError("node_update is the bf16 tcgen05 path; fp32 features go through fused_mlp")
+    W0 = params[0]
+    if W0.shape != (D_LATENT, 2 * D_LATENT) or v.shape != agg.shape or v.shape[-1] != D_LATENT or v.shape[0] == 0:
+        raise _cabi.HgnError(f"node_update is specialised for latent 128 and one aggregate: W0 {tuple(W0.shape)}, v {tuple(v.shape)}")
+    v, agg = v.contiguous(), agg.contiguous()
+    with torch.cuda.device(v.device):
+        packed = _pack_weights(packed_cache, torch.bfloat16, 2, params)
+    return _NodeUpdate.apply(v, agg, *params, packed)
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     """fp32 column sums of ``x[rows, D]`` (deterministic)."""
     lib = _cabi.load()

@@ -174,6 +174,21 @@ int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, con
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- node update, one 'sum' aggregate (HGN_BF16 only) -- src/migration/graphnet.py:34-48 with S = 1, k = 1 -------------
+ *     v' = v + LN(W2 relu(W1 relu(Wv v + Wa agg + b0) + b1) + b2),   W0 = [Wv | Wa] = node_model_cross.0.layers.linear_0.weight
+ * `packed` is the hgn_mlp_pack blob of the node MLP with n_chunks = 2.  q[N,128] (caller-owned, bf16) receives agg Wa^T, which the
+ * backward reads again.  Runs on the projected edge kernels: q plays the role of a node table gathered through the identity.
+ * Backward (activations recomputed): grad_v = d loss / d v (residual branch included), grad_agg = d loss / d agg, and every
+ * parameter gradient (fp32, overwritten, fixed-order reductions).  num_nodes must be > 0 for the backward. */
+int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed,
+                            void* q, void* out, void* stream);
+size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes);
+int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed,
+                             const void* grad_out, void* grad_v, void* grad_agg,
+                             float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
+                             float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- column sums ------------------------------------------------------------------------------
  * out[D] (fp32) = sum over rows of x[rows, D]; two-stage fixed-order reduction (LayerNorm beta / bias
  * gradients).  D must be a multiple of 4 and <= 1024. */

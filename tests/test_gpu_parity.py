@@ -316,6 +316,45 @@ def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg):
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
 
+def _bf16_emulated_projected_node(v, agg, w):
+    """Rounding points of ops.node_update: bf16 operands, bf16 q = agg Wa^T table, bf16 H1/H2."""
+    W0, b0, W1, b1, W2, b2, g, b = w
+    rd = lambda t: t.to(torch.bfloat16).float()
+    q = rd(agg @ rd(W0[:, 128:]).t())
+    h = torch.relu(q + v @ rd(W0[:, :128]).t() + b0)
+    h = torch.relu(rd(h) @ rd(W1).t() + b1)
+    return v + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
+
+
+@pytest.mark.parametrize("n_nodes", [1, 63, 128, 129, 1000, 1600, 40000])
+def test_projected_node_update_vs_bf16_emulation(n_nodes):
+    """ops.node_update (aggregate projection + the fused edge kernels driven with identity indices) against torch arithmetic
+    with the same rounding points, on ragged tile counts; run twice for bit determinism."""
+    torch.manual_seed(n_nodes)
+    w = _random_mlp_weights(2, 13)
+    v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    a0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    gup = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    runs = []
+    for _ in range(2):
+        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+        v, agg = v0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+        out = ops.node_update(params, {}, v, agg)
+        out.backward(gup)
+        runs.append([out.detach(), v.grad, agg.grad] + [p.grad for p in params])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    wr = [p.detach().clone().requires_grad_(True) for p in params]
+    vf, af = v0.float().requires_grad_(True), a0.float().requires_grad_(True)
+    ref = _bf16_emulated_projected_node(vf, af, wr)
+    ref.backward(gup.float())
+    assert rel_err(out.float(), ref) < 1e-2
+    assert rel_l2(v.grad.float(), vf.grad) < 1e-2 and rel_l2(agg.grad.float(), af.grad) < 1.5e-2
+    for a, b in zip(params, wr):
+        assert rel_l2(a.grad, b.grad) < 1.5e-2
+
+
 def test_projected_edge_update_is_deterministic():
     torch.manual_seed(3)
     w = _random_mlp_weights(3, 11)
