@@ -22,6 +22,7 @@
 // TMEM (512 columns): chain accumulator [0,128) | dW2 [128,256) | dW1 [256,384) | dWe [384,512).
 // Nothing but d e and G0 (and per-CTA fp32 partials at the end) is written to HBM; the previous design wrote six
 // [E,128] workspaces per layer.  All reductions have a fixed order (per-CTA partials, then a sequential sum over CTAs).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "tile_common.cuh"
@@ -193,7 +194,8 @@ __device__ __forceinline__ void stamp(const EdgeBwdArgs& a, int64_t t, int slot)
 }
 
 __global__ void __launch_bounds__(kEbThreads, 1)
-edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, EdgeBwdArgs a) {
+edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, EdgeBwdArgs a,
+                   const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_g0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();
@@ -210,7 +212,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     load_weight_block(sbase + kEbW2, reinterpret_cast<const __nv_bfloat16*>(packed + P.w2), kD, tid, kEbThreads);
     cp_async_commit();
     if (tid == 0) {
-      mbar_init(&bars[kEbFull], kEbProdThreads);
+      mbar_init(&bars[kEbFull], 1);                           // one arrive.expect_tx per tile, completed by the TMA bytes
       mbar_init(&bars[kEbFree], 1);
       mbar_init(&bars[kEbAcc], 1);
       mbar_init(&bars[kEbEpi], kEbEpiThreads);
@@ -234,17 +236,15 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
   if (warp == 8 || warp == 9) {
     // =============================== producers =========================================================
     const int ptid = tid - kEbEpiThreads, pw = warp - 8;
+    // edge rows of tile t: two TMA boxes (128 rows x 64 columns, 128B-swizzled) into the tile's S buffer
     auto load_e = [&](int64_t t) {
-      const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTile;
-      const uint32_t dst = buf(0, t);
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) {
-        const int qd = ptid + kEbProdThreads * j, row = qd >> 4, c16 = qd & 15;
-        const int64_t grow = row0 + row;
-        const bool valid = grow < rows;
-        cp_async16_zfill(dst + (c16 >> 3) * kPanel + sw128_chunk(row, c16 & 7), a.edge + (valid ? grow : 0) * kD + c16 * 8, valid);
+      if (ptid == 0) {
+        const uint32_t dst = buf(0, t);
+        const int y = int((blockIdx.x + t * gridDim.x) * kTile);
+        mbar_expect_tx(&bars[kEbFull], kChunkBytes);
+        tma_load_2d(dst, &tm_e, 0, y, &bars[kEbFull]);
+        tma_load_2d(dst + kPanel, &tm_e, 64, y, &bars[kEbFull]);
       }
-      cp_async_commit();
     };
     // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..); lane l reads the 16-byte piece l & 7
     // (8 columns) of rows 4 i + (l >> 3).  Each lane keeps fp32 partials over ALL its tiles; the four row groups are
@@ -269,12 +269,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc8[2 * j] += t[j].x; acc8[2 * j + 1] += t[j].y; }
     };
-    if (my_tiles > 0) {
-      load_e(0);
-      cp_async_wait<0>();
-      fence_async_smem();
-      mbar_arrive(&bars[kEbFull]);
-    }
+    if (my_tiles > 0) load_e(0);
     for (int64_t t = 0; t < my_tiles; ++t) {
       const uint32_t par = uint32_t(t) & 1;
       const bool more = t + 1 < my_tiles;
@@ -308,17 +303,20 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       if (ptid == 0) stamp(a, t, 22);
       if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) takes the next tile's edge rows
       if (ptid == 0) stamp(a, t, 23);
-      mbar_wait(&bars[kEbG + 2], par, 53);                   // dH1' is in buffer C
-      if (more) {                                            // publish the edge rows first: the next tile's step 0 waits on them
-        cp_async_wait<0>();
-        fence_async_smem();
-        mbar_arrive(&bars[kEbFull]);
+      mbar_wait(&bars[kEbG + 2], par, 53);                   // dH1' = G0 is in buffer C (and fenced for the async proxy)
+      if (ptid == 0 && !(a.ablate & 2)) {                    // G0 goes to HBM straight from the operand buffer
+        const int y = int((blockIdx.x + t * gridDim.x) * kTile);
+        tma_store_2d(&tm_g0, buf(3, t), 0, y);
+        tma_store_2d(&tm_g0, buf(3, t) + kPanel, 64, y);
+        tma_store_commit();
       }
       if (ptid == 0) stamp(a, t, 24);
       colsum(buf(3, t), cs[2]);                              // dH1'
+      if (ptid == 0) tma_store_wait_read<0>();               // the store has read the buffer before E1 of the next tile reuses it
       mbar_arrive(&bars[kEbCs + 2]);
       if (ptid == 0) stamp(a, t, 25);
     }
+    if (ptid == 0) tma_store_wait<0>();
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -635,11 +633,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         // indices of the next tile's row (an L2 hit: the producers touched them a tile ago); first used by the next E0
         si = 0; ri = 0;
         if (vnext) { si = row_index(a.senders, gnext); ri = row_index(a.receivers, gnext); }
-        if (valid && !(a.ablate & 2)) {
-          __nv_bfloat16* g0row = a.grad_pre0 + grow * kD + hh * 64;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) stg256(g0row + 16 * k, o + 8 * k);
-        }
       }
       // ---- E5: d e = dH1' We + dO -> HBM -------------------------------------------------------------------------------
       {
@@ -798,6 +791,7 @@ int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packe
   return HGN_OK;
 }
 
+int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // edge_fwd_tc.cu
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
                        const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st);   // edge_fwd_tc.cu
 
@@ -866,9 +860,12 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
     a.timeline = tl_dev;
   }
   const int64_t tiles = ceil_div(rows, kTile);
+  CUtensorMap tm_e, tm_g0;                       // rows == 0: maps over one (never accessed) row keep the encoder happy
+  if (int rc = make_rows_tensor_map(&tm_e, dense != nullptr ? dense : workspace, rows > 0 ? rows : 1)) return rc;
+  if (int rc = make_rows_tensor_map(&tm_g0, grad_pre0 != nullptr ? grad_pre0 : workspace, rows > 0 ? rows : 1)) return rc;
   {
     HGN_TIMED(name, st);
-    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a);
+    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a, tm_e, tm_g0);
   }
   HGN_LAUNCH_OK(name);
   if (a.timeline != nullptr) {
