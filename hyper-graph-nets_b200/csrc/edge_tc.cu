@@ -172,7 +172,7 @@ constexpr uint32_t kEbBars = kEbParams + 5 * kD * 4;
 constexpr uint32_t kEbSmem = kEbBars + 128;                        // 232 064 B of the 232 448 available
 // kEbG + k / kEbCs + k (k = 0 dY, 1 dH2', 2 dH1'): one barrier per tile-in-buffer hand-over, so each completes exactly one
 // phase per tile and no waiter can fall two phases behind (a parity wait cannot tell phase n from phase n + 2)
-enum { kEbFull = 0, kEbFree = 1, kEbAcc = 2, kEbEpi = 3, kEbG = 4, kEbCs = 7, kEbTmem = 10, kEbAfree = 11 };
+enum { kEbFull = 0, kEbWg = 1, kEbAcc = 2, kEbEpi = 3, kEbG = 4, kEbCs = 7, kEbTmem = 10, kEbAfree = 11, kEbFinal = 12, kEbDe = 13, kEbDeFree = 14, kEbG0Free = 15 };
 
 struct EdgeBwdArgs {
   const __nv_bfloat16 *edge, *proj_s, *proj_r;
@@ -195,7 +195,8 @@ __device__ __forceinline__ void stamp(const EdgeBwdArgs& a, int64_t t, int slot)
 
 __global__ void __launch_bounds__(kEbThreads, 1)
 edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ packed, EdgeBwdArgs a,
-                   const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_g0) {
+                   const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_g0,
+                   const __grid_constant__ CUtensorMap tm_de) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();
@@ -213,7 +214,11 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     cp_async_commit();
     if (tid == 0) {
       mbar_init(&bars[kEbFull], 1);                           // one arrive.expect_tx per tile, completed by the TMA bytes
-      mbar_init(&bars[kEbFree], 1);
+      mbar_init(&bars[kEbWg], 1);
+      mbar_init(&bars[kEbFinal], 1);
+      mbar_init(&bars[kEbDe], kEbEpiThreads);
+      mbar_init(&bars[kEbDeFree], 1);
+      mbar_init(&bars[kEbG0Free], 1);
       mbar_init(&bars[kEbAcc], 1);
       mbar_init(&bars[kEbEpi], kEbEpiThreads);
       mbar_init(&bars[kEbAfree], kEbEpiThreads);
@@ -236,16 +241,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
   if (warp == 8 || warp == 9) {
     // =============================== producers =========================================================
     const int ptid = tid - kEbEpiThreads, pw = warp - 8;
-    // edge rows of tile t: two TMA boxes (128 rows x 64 columns, 128B-swizzled) into the tile's S buffer
-    auto load_e = [&](int64_t t) {
-      if (ptid == 0) {
-        const uint32_t dst = buf(0, t);
-        const int y = int((blockIdx.x + t * gridDim.x) * kTile);
-        mbar_expect_tx(&bars[kEbFull], kChunkBytes);
-        tma_load_2d(dst, &tm_e, 0, y, &bars[kEbFull]);
-        tma_load_2d(dst + kPanel, &tm_e, 64, y, &bars[kEbFull]);
-      }
-    };
     // column sums of a bf16 tile in a buffer: warp pw owns panel pw (columns 64 pw ..); lane l reads the 16-byte piece l & 7
     // (8 columns) of rows 4 i + (l >> 3).  Each lane keeps fp32 partials over ALL its tiles; the four row groups are
     // combined once, after the last tile (fixed order).
@@ -268,6 +263,16 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc8[2 * j] += t[j].x; acc8[2 * j + 1] += t[j].y; }
+    };
+    // edge rows of tile t: two TMA boxes (128 rows x 64 columns, 128B-swizzled) into the tile's S buffer
+    auto load_e = [&](int64_t t) {
+      if (ptid == 0) {
+        const uint32_t dst = buf(0, t);
+        const int y = int((blockIdx.x + t * gridDim.x) * kTile);
+        mbar_expect_tx(&bars[kEbFull], kChunkBytes);
+        tma_load_2d(dst, &tm_e, 0, y, &bars[kEbFull]);
+        tma_load_2d(dst + kPanel, &tm_e, 64, y, &bars[kEbFull]);
+      }
     };
     if (my_tiles > 0) load_e(0);
     for (int64_t t = 0; t < my_tiles; ++t) {
@@ -299,10 +304,8 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       mbar_wait(&bars[kEbG + 1], par, 51);
       colsum(buf(2, t), cs[1]);                              // dH2'
       mbar_arrive(&bars[kEbCs + 1]);
-      mbar_wait(&bars[kEbAfree], par, 52);                   // step 4 has completed and every epilogue thread has read H1 back:
-      if (ptid == 0) stamp(a, t, 22);
+      mbar_wait(&bars[kEbAfree], par, 52);                   // H1 has been read back and the dW1 MMAs are done:
       if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) takes the next tile's edge rows
-      if (ptid == 0) stamp(a, t, 23);
       mbar_wait(&bars[kEbG + 2], par, 53);                   // dH1' = G0 is in buffer C (and fenced for the async proxy)
       if (ptid == 0 && !(a.ablate & 2)) {                    // G0 goes to HBM straight from the operand buffer
         const int y = int((blockIdx.x + t * gridDim.x) * kTile);
@@ -310,11 +313,9 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         tma_store_2d(&tm_g0, buf(3, t) + kPanel, 64, y);
         tma_store_commit();
       }
-      if (ptid == 0) stamp(a, t, 24);
-      colsum(buf(3, t), cs[2]);                              // dH1'
+      colsum(buf(3, t), cs[2]);
       if (ptid == 0) tma_store_wait_read<0>();               // the store has read the buffer before E1 of the next tile reuses it
       mbar_arrive(&bars[kEbCs + 2]);
-      if (ptid == 0) stamp(a, t, 25);
     }
     if (ptid == 0) tma_store_wait<0>();
 #pragma unroll
@@ -368,11 +369,14 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         stamp(a, t, 2);
         wait_epi(); stamp(a, t, 3); chain(A, sbase + kEbW1, false);  mma_commit(&bars[kEbAcc]);                        // 1: H1 W1^T
         wait_epi(); stamp(a, t, 4); chain(B, sbase + kEbW2, false);  mma_commit(&bars[kEbAcc]);                        // 2: H2 W2^T
+        // steps 3 and 4 commit after their weight-gradient MMAs: the epilogue warps spend that time on the LayerNorm vector
+        // column sums anyway, and phases E3 / E4 overwrite buffers those MMAs read.  Step 5 commits right after the chain.
         wait_epi(); stamp(a, t, 5); chain(C, sbase + kEbW2, true);   wgrad(dW2, C, B, first); mma_commit(&bars[kEbAcc]);   // 3: dY W2 ; dW2
         wait_epi(); stamp(a, t, 6); chain(B, sbase + kEbW1, true);   wgrad(dW1, B, A, first); mma_commit(&bars[kEbAcc]);   // 4: dH2' W1 ; dW1
-        wait_epi(); stamp(a, t, 7); chain(C, sbase + kEbWe, true);   wgrad(dWe, C, S, first); mma_commit(&bars[kEbAcc]);   // 5: dH1' We ; dWe
+        wait_epi(); stamp(a, t, 7); chain(C, sbase + kEbWe, true);   mma_commit(&bars[kEbAcc]); wgrad(dWe, C, S, first);   // 5: dH1' We ; dWe
         stamp(a, t, 8);
       }
+      if (my_tiles > 0) mma_commit(&bars[kEbFinal]);          // every MMA of this CTA, for the accumulator drain
     }
   } else {
     // =============================== epilogue ============================================================
@@ -447,7 +451,11 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 64; ++j) pq[j] = 0u;
         if (ld_on) load_tables(si, ri, pq);
-        if (t > 0) wait_cs(1, t - 1);                           // the producers' dH2' column sum has left this buffer
+        if (t > 0) {
+          wait_cs(1, t - 1);                                    // the producers' dH2' column sum has left this buffer
+          if (tid == 0) { tma_store_wait_read<0>(); mbar_arrive(&bars[kEbDeFree]); }   // ... and so has the TMA store of d e
+          mbar_wait(&bars[kEbDeFree], uint32_t(t - 1) & 1, 73);
+        }
         wait_acc(100); if (tid == 0) stamp(a, t, 10);
         uint32_t h[32];
 #pragma unroll
@@ -483,12 +491,10 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
           for (int k = 0; k < 4; ++k) ldg256_l1(garow + 16 * k, dq + 32 + 8 * k);
         }
-        // one rounding to bf16, the value every later use sees.  Consumed here, before the phase's proxy fence: a fence
-        // with global loads still in flight waits for them
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dreg[j] = add_bf16x2(dq[j], dq[32 + j]);
         // ---- E1: H2 = relu(H1 W1^T + b1) -> B -------------------------------------------------------------------
-        if (t > 0) wait_cs(2, t - 1);                           // previous tile's dH1' column sum has left this buffer
+        if (t > 0) {
+          wait_cs(2, t - 1);                                    // previous tile's dH1' column sum has left this buffer
+        }
         wait_acc(101); if (tid == 0) stamp(a, t, 12);
         uint32_t h[32];
 #pragma unroll
@@ -507,6 +513,9 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         store_row(B, h);
         if (tid == 0) stamp(a, t, 13);
         done(-1);
+        // one rounding to bf16, the value every later use sees (EXPERIMENT: consumed after the phase's fence)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dreg[j] = add_bf16x2(dq[j], dq[32 + j]);
       }
       // ---- E2: y = H2 W2^T + b2 ; LayerNorm forward statistics and backward -> dY -> C --------------------------------
       uint32_t preg[32];                                        // dO * yhat (bf16): gamma-gradient terms, summed after the phase
@@ -637,7 +646,6 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       // ---- E5: d e = dH1' We + dO -> HBM -------------------------------------------------------------------------------
       {
         wait_acc(105); if (tid == 0) stamp(a, t, 20);
-        __nv_bfloat16* derow = a.grad_edge + (valid ? grow : 0) * kD + hh * 64;
         uint32_t v0[32], v1[32];
         tmem_ld32(acc, v0);
         tmem_ld32(acc + 32, v1);
@@ -654,15 +662,28 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           o[j] = pack_bf16(x0.x, x0.y);
           o[16 + j] = pack_bf16(x1.x, x1.y);
         }
-        if (valid && !(a.ablate & 2)) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) stg256(derow + 16 * k, o + 8 * k);
+        // staged in buffer B (dH2' is dead: the chain commit above came after the dW1 MMAs) and stored by the producers' TMA
+        store_row(B, o);
+        fence_async_smem();
+        mbar_arrive(&bars[kEbDe]);
+        if (tid == 0) {                                         // one thread stores the staged tile once all 256 rows are in
+          mbar_wait(&bars[kEbDe], uint32_t(t) & 1, 77);
+          if (!(a.ablate & 2)) {
+            const int y = int((blockIdx.x + t * gridDim.x) * kTile);
+            tma_store_2d(&tm_de, B, 0, y);
+            tma_store_2d(&tm_de, B + kPanel, 64, y);
+            tma_store_commit();
+          }
+          stamp(a, t, 21);
         }
-        if (tid == 0) stamp(a, t, 21);
       }
     }
+    if (tid == 0) tma_store_wait<0>();
     // ---- drain the weight-gradient accumulators and the LayerNorm vector partials ---------------------------------------
-    // (the last wait_acc above saw the commit that followed every MMA of this CTA)
+    if (my_tiles > 0) {
+      mbar_wait(&bars[kEbFinal], 0, 75);
+      fence_after_sync();
+    }
 #pragma unroll 1
     for (int z = 0; z < 3; ++z) {
       const uint32_t col0 = 384u - 128u * uint32_t(z);           // z = 0: dWe, 1: dW1, 2: dW2
@@ -860,12 +881,13 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
     a.timeline = tl_dev;
   }
   const int64_t tiles = ceil_div(rows, kTile);
-  CUtensorMap tm_e, tm_g0;                       // rows == 0: maps over one (never accessed) row keep the encoder happy
+  CUtensorMap tm_e, tm_g0, tm_de;                       // rows == 0: maps over one (never accessed) row keep the encoder happy
   if (int rc = make_rows_tensor_map(&tm_e, dense != nullptr ? dense : workspace, rows > 0 ? rows : 1)) return rc;
   if (int rc = make_rows_tensor_map(&tm_g0, grad_pre0 != nullptr ? grad_pre0 : workspace, rows > 0 ? rows : 1)) return rc;
+  if (int rc = make_rows_tensor_map(&tm_de, grad_dense != nullptr ? grad_dense : workspace, rows > 0 ? rows : 1)) return rc;
   {
     HGN_TIMED(name, st);
-    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a, tm_e, tm_g0);
+    edge_bwd_tc_kernel<<<unsigned(L.grid), kEbThreads, kEbSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a, tm_e, tm_g0, tm_de);
   }
   HGN_LAUNCH_OK(name);
   if (a.timeline != nullptr) {
