@@ -140,7 +140,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         from hgn_b200 import partition
-        return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler)
+        return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler,
+                                           dominant_kernel_roofline)
 
     data = build_inputs(GRID_W, GRID_H, LAYERS)
     n, e = data["n"], data["e"]

@@ -129,11 +129,12 @@ class GraphNet(nn.Module):
         aggregates = self._aggregates(edge_sets, v.shape[0], v.device)
         sources = [v] + aggregates
         params = _mlp_parameters(model, v.shape[1] * len(sources), v)
-        if (len(aggregates) == 1 and len(node_features) == 1 and rows > 0 and v.dtype == torch.bfloat16
-                and aggregates[0].dtype == torch.bfloat16 and v.shape[1] == ops.D_LATENT):
+        if (len(aggregates) == 1 and rows > 0 and v.dtype == torch.bfloat16 and aggregates[0].dtype == torch.bfloat16
+                and v.shape[1] == ops.D_LATENT):
             # throughput mode, one aggregate: the aggregate's block of the first linear is applied per node row and the
-            # projected edge kernels do the rest (ops._NodeUpdate)
-            return ops.node_update(params, _packed_cache(model), v, aggregates[0])
+            # projected edge kernels do the rest (ops._NodeUpdate).  With hyper / ghost rows in the list only the target's
+            # slice of the aggregate is consumed, like the reference's agg_features[:N] / [N:] (graphnet.py:45,105).
+            return ops.node_update(params, _packed_cache(model), node_features[target], aggregates[0][offset: offset + rows])
         chunks = [ops.ChunkSpec(i, None, offset) for i in range(len(sources))]
         return ops.fused_mlp(params, _packed_cache(model), sources, chunks, rows=rows, resid_source=0, resid_offset=offset)
 

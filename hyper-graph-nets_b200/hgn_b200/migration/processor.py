@@ -3,7 +3,10 @@
 Precision: the reference computes in fp32.  ``precision='fp32'`` keeps fp32 storage and fp32 FFMA
 arithmetic (parity mode, 1e-5 relative).  ``precision='bf16'`` converts the latents to bf16 once on
 entry, runs every block on the bf16 tcgen05 kernels (fp32 accumulation, fp32 LayerNorm/residual
-arithmetic) and converts back on exit (throughput mode, 2e-2 relative).  Select it per module
+arithmetic) and converts the NODE latents back on exit (throughput mode, 2e-2 relative); the edge latents
+are returned in bf16 -- nothing downstream in the reference reads them (decoder.py:15-16 decodes
+``node_features[0]`` only) and an [E,128] fp32 round trip per step would cost two full HBM passes.  Set
+``processor.restore_edge_dtype = True`` to get them back in the caller's dtype.  Select the mode per module
 (``processor.precision = 'bf16'``), globally (``hgn_b200.set_precision``) or with the environment
 variable ``HGN_B200_PRECISION``; no config-schema change is needed.
 """
@@ -28,6 +31,7 @@ class Processor(nn.Module):
                            message_passing_aggregator=message_passing_aggregator, edge_sets=edge_sets)
             for _ in range(message_passing_steps)])
         self.precision = None       # None -> hgn_b200.config.precision()
+        self.restore_edge_dtype = False
 
     def forward(self, latent_graph: MultiGraph) -> MultiGraph:
         precision = self.precision or config.precision()
@@ -44,4 +48,6 @@ class Processor(nn.Module):
         graph = self.graphnet_blocks(graph)
         for i in range(len(graph.node_features)):
             graph.node_features[i] = graph.node_features[i].to(in_dtype)
+        if not getattr(self, 'restore_edge_dtype', False):
+            return graph
         return graph._replace(edge_sets=[es._replace(features=es.features.to(in_dtype)) for es in graph.edge_sets])

@@ -219,7 +219,7 @@ class PartitionedProcessor(torch.nn.Module):
             graph.node_features[1] = halo_exchange(graph.node_features[0], self.plan)
             graph = block(graph)
         out_nodes = graph.node_features[0].to(in_dtype)
-        return out_nodes, [es._replace(features=es.features.to(in_dtype)) for es in graph.edge_sets]
+        return out_nodes, list(graph.edge_sets)      # edge latents stay in the compute dtype (see Processor.forward)
 
 
 def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
@@ -238,7 +238,7 @@ def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
 # ------------------------------------------------------------------------------------------------------
 # multi-GPU benchmark (bench.py --gpus N under torchrun)
 # ------------------------------------------------------------------------------------------------------
-def bench_partitioned(args, world, rank, dev, width, height, layers, metric, unit, peaks, clock_sampler_cls):
+def bench_partitioned(args, world, rank, dev, width, height, layers, metric, unit, peaks, clock_sampler_cls, roofline_fn=None):
     import json
     import os
     from . import ops, synthetic
@@ -295,10 +295,15 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
 
     for _ in range(max(args.warmup, 3)):
         step(v_dev.detach(), e_dev.detach())
+    from . import _cabi
     launches0 = ops.launch_count
+    _cabi.profile(True)
     with clock_sampler_cls(dev.index) as clocks:
         ms_per_step = timed(lambda: step(v_dev.detach(), e_dev.detach()), args.steps)
     launches = ops.launch_count - launches0
+    kernels = _cabi.profile_report()
+    _cabi.profile(False)
+    roofline = roofline_fn(kernels, args.steps, int(lg.edge_ids.numel()), int(lg.owned.numel()), peaks) if roofline_fn else None
 
     def step_e2e():
         loss = step(v_host.to(dev, non_blocking=True), e_host.to(dev, non_blocking=True))
@@ -323,6 +328,7 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
             "e2e": {"value": e_total * layers / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int((v_host.numel() + e_host.numel()) * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None,
+            "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
         }))
     dist.destroy_process_group()
