@@ -222,7 +222,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
         "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, "
                                "processor fwd+bwd", "nodes": n, "edges": e, "layers": LAYERS, "latent": LATENT,
-                   "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none"},
+                   "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none",
+                   "backward": ops.backward_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -249,7 +250,8 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
     # name -> (rows per launch, algorithmic flops per row, executed flops per row)
     tensor = {
         "edge_fwd_tc": (e, F_EDGE, 6 * d2), "edge_bwd_tc": (e, 2 * F_EDGE, 18 * d2),
-        "node_fwd_tc": (n, F_NODE_SUM, 6 * d2), "node_bwd_tc": (n, 2 * F_NODE_SUM, 18 * d2),
+        "edge_bwd_stash_tc": (e, 2 * F_EDGE, 14 * d2),
+        "node_fwd_tc": (n, F_NODE_SUM, 6 * d2), "node_bwd_tc": (n, 2 * F_NODE_SUM, 18 * d2), "node_bwd_stash_tc": (n, 2 * F_NODE_SUM, 14 * d2),
         "mlp_tile_tc_fwd": (n, F_NODE_SUM, F_NODE_SUM), "mlp_tile_tc_bwd": (n, F_NODE_SUM, 2 * F_NODE_SUM),
         "mlp_wgrad_tc": (n, F_NODE_SUM, F_NODE_SUM),
     }.get(top["name"])

@@ -89,16 +89,18 @@ size_t edge_project_backward_workspace_tc(int64_t num_nodes);
 int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
                              float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st);
+                           const int32_t* receivers, const void* packed, void* out, void* h1, void* h2, cudaStream_t st);
 size_t edge_update_backward_workspace_tc(int64_t num_edges);
 int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
-                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
-                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                            const int32_t* receivers, const void* h1, const void* h2, const void* packed, const void* grad_out,
+                            const void* grad_agg, void* grad_edge, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
+                            float* gb2, float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, cudaStream_t st);
+int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, void* h1, void* h2,
+                           cudaStream_t st);
 size_t node_update_backward_workspace_tc(int64_t num_nodes);
-int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed, const void* grad_out,
+int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1, const void* h2,
+                            const void* packed, const void* grad_out,
                             void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
                             float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
@@ -213,12 +215,14 @@ extern "C" int hgn_edge_project_backward(int dtype, int64_t num_nodes, const voi
 }
 
 extern "C" int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                                       const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* stream) {
+                                       const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* h1, void* h2,
+                                       void* stream) {
   HGN_BF16_ONLY("edge_update_forward");
   HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_forward: num_edges=%lld", (long long)num_edges);
   if (num_edges == 0) return HGN_OK;
   HGN_CHECK_ARG(edge && proj_s && proj_r && senders && receivers && packed && out, "edge_update_forward: null pointer");
-  return edge_update_forward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, out, static_cast<cudaStream_t>(stream));
+  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "edge_update_forward: h1 and h2 must be given together");
+  return edge_update_forward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, out, h1, h2, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges) {
@@ -227,7 +231,8 @@ extern "C" size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t nu
 }
 
 extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                                        const int32_t* senders, const int32_t* receivers, const void* packed, const void* grad_out,
+                                        const int32_t* senders, const int32_t* receivers, const void* h1, const void* h2,
+                                        const void* packed, const void* grad_out,
                                         const void* grad_agg, void* grad_edge, void* grad_pre0, float* grad_W0, float* grad_b0,
                                         float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma,
                                         float* grad_beta, void* workspace, size_t workspace_bytes, void* stream) {
@@ -235,20 +240,22 @@ extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void
   HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_backward: num_edges=%lld", (long long)num_edges);
   HGN_CHECK_ARG(packed && workspace && grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta,
                 "edge_update_backward: null pointer");
-  HGN_CHECK_ARG(num_edges == 0 || (edge && proj_s && proj_r && senders && receivers && grad_edge && grad_pre0),
+  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "edge_update_backward: h1 and h2 must be given together");
+  HGN_CHECK_ARG(num_edges == 0 || (edge && receivers && grad_edge && grad_pre0 && (h1 || (proj_s && proj_r && senders))),
                 "edge_update_backward: null pointer");
-  return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, grad_out, grad_agg, grad_edge, grad_pre0,
+  return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, h1, h2, packed, grad_out, grad_agg, grad_edge, grad_pre0,
                                  grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes,
                                  static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out,
-                                       void* stream) {
+                                       void* h1, void* h2, void* stream) {
   HGN_BF16_ONLY("node_update_forward");
   HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "node_update_forward: num_nodes=%lld", (long long)num_nodes);
   if (num_nodes == 0) return HGN_OK;
   HGN_CHECK_ARG(v && agg && packed && q && out, "node_update_forward: null pointer");
-  return node_update_forward_tc(num_nodes, v, agg, packed, q, out, static_cast<cudaStream_t>(stream));
+  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "node_update_forward: h1 and h2 must be given together");
+  return node_update_forward_tc(num_nodes, v, agg, packed, q, out, h1, h2, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes) {
@@ -256,15 +263,17 @@ extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t nu
   return node_update_backward_workspace_tc(num_nodes);
 }
 
-extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed,
+extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1,
+                                        const void* h2, const void* packed,
                                         const void* grad_out, void* grad_v, void* grad_agg, float* grad_W0, float* grad_b0, float* grad_W1,
                                         float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   HGN_BF16_ONLY("node_update_backward");
   HGN_CHECK_ARG(num_nodes > 0 && num_nodes < (int64_t(1) << 31), "node_update_backward: num_nodes=%lld", (long long)num_nodes);
-  HGN_CHECK_ARG(v && agg && q && packed && grad_out && grad_v && grad_agg && workspace, "node_update_backward: null pointer");
+  HGN_CHECK_ARG(v && agg && packed && grad_out && grad_v && grad_agg && workspace, "node_update_backward: null pointer");
+  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr) && (h1 || q), "node_update_backward: needs q (recompute) or h1 and h2 (stash)");
   HGN_CHECK_ARG(grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta, "node_update_backward: null pointer");
-  return node_update_backward_tc(num_nodes, v, agg, q, packed, grad_out, grad_v, grad_agg, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
+  return node_update_backward_tc(num_nodes, v, agg, q, h1, h2, packed, grad_out, grad_v, grad_agg, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
                                  grad_gamma, grad_beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

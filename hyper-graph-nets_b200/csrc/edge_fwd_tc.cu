@@ -39,6 +39,8 @@ struct EdgeFwdArgs {
   const __nv_bfloat16 *proj_s, *proj_r;     // per-node tables; proj_r may be null
   const int32_t *senders, *receivers;       // null = identity (row i gathers table row i)
   int w0_chunks, w0_chunk0;                 // W0 is [128][128 w0_chunks]; the dense input multiplies chunk w0_chunk0
+  __nv_bfloat16 *h1, *h2;                   // optional [rows,128] stash of the hidden activations for the backward (null = none)
+  long long* timeline;                      // development (HGN_TC_ABLATE bit 64): clock64 stamps of block 0, [tile][32]
 };
 
 __global__ void __launch_bounds__(kEfThreads, 1)
@@ -77,6 +79,7 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
   const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   auto stage_addr = [&](int64_t it) -> uint32_t { return sbase + kEfStage + uint32_t(it % kEfStages) * kChunkBytes; };
   auto tile_row0 = [&](int64_t it) -> int64_t { return (blockIdx.x + it * gridDim.x) * kTile; };
+  auto stamp = [&](int64_t it, int slot) { if (a.timeline != nullptr && blockIdx.x == 0 && it < 12) a.timeline[it * 32 + slot] = clock64(); };
 
   if (warp == 17) {
     // =============================== loader warp ==========================================================
@@ -102,12 +105,14 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         const int64_t j = i - kEfStages;
         mbar_wait(&bars[kEfOut + int(j & 1)], uint32_t(j >> 1) & 1, 30);
         if (lane == 0) {
+          stamp(j, 20);
           const uint32_t src = stage_addr(j);
           const int y = int(tile_row0(j));
           tma_store_2d(&tm_out, src, 0, y);
           tma_store_2d(&tm_out, src + kPanel, 64, y);
           tma_store_commit();
           tma_store_wait_read<0>();
+          stamp(j, 21);
         }
         __syncwarp();
       }
@@ -116,6 +121,7 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         const int st = int(i % kEfStages);
         const uint32_t dst = stage_addr(i);
         const int y = int(tile_row0(i));
+        stamp(i, 22);
         mbar_expect_tx(&bars[kEfFull + st], kChunkBytes);
         tma_load_2d(dst, &tm_in, 0, y, &bars[kEfFull + st]);
         tma_load_2d(dst + kPanel, &tm_in, 64, y, &bars[kEfFull + st]);
@@ -143,33 +149,48 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
       uint32_t epi_phase[2] = {0, 0};
-      auto wait_epi = [&](int s) {
-        mbar_wait(&bars[kEfEpi + s], epi_phase[s]++ & 1, 31 + s);
-        fence_after_sync();
-      };
       auto gemm_ts = [&](int s, uint32_t b_addr) {       // acc_s = A_s (TMEM, bf16) * B^T
         const uint32_t acc = tmem_base + s * 256, aop = acc + 128;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) mma_ts(acc, aop + ks * 8, sdesc_kmajor(b_addr + (ks >> 2) * kPanel + (ks & 3) * 32), idesc, ks != 0);
         mma_commit(&bars[kEfAcc + s]);
       };
-      for (int64_t p = 0; p < my_tiles; p += 2) {
-        const int n = my_tiles - p >= 2 ? 2 : 1;
-        for (int s = 0; s < n; ++s) {
-          const int64_t it = p + s;
-          if (it >= 2) wait_epi(s);                      // the slot's previous tile has left the accumulator
-          mbar_wait(&bars[kEfFull + int(it % kEfStages)], uint32_t(it / kEfStages) & 1, 33);
-          fence_after_sync();
-          const uint32_t acc = tmem_base + s * 256, a_addr = stage_addr(it), b_addr = sbase + kEfWe;
+      // Event driven: each slot (tiles s, s + 2, ...) advances through GEMM0 / GEMM1 / GEMM2 as soon as ITS inputs are ready
+      // (stage loaded and accumulator drained / previous phase's activations written), so a slot waiting for a tile load
+      // never holds the other one back -- a fixed issue order locks the two slots into step and halves the prefetch lead.
+      int64_t slot_tile[2] = {0, 1};
+      int slot_step[2] = {0, 0};
+      uint32_t idle = 0;
+      while (slot_tile[0] < my_tiles || slot_tile[1] < my_tiles) {
+        bool progressed = false;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t koff = (ks >> 2) * kPanel + (ks & 3) * 32;
-            mma_ss(acc, sdesc_kmajor(a_addr + koff), sdesc_kmajor(b_addr + koff), idesc, ks != 0);
+        for (int s = 0; s < 2; ++s) {
+          const int64_t it = slot_tile[s];
+          if (it >= my_tiles) continue;
+          const int k = slot_step[s];
+          const bool need_epi = k > 0 || it >= 2;
+          if (need_epi && !mbar_test(&bars[kEfEpi + s], epi_phase[s] & 1)) continue;
+          if (k == 0 && !mbar_test(&bars[kEfFull + int(it % kEfStages)], uint32_t(it / kEfStages) & 1)) continue;
+          if (need_epi) ++epi_phase[s];
+          fence_after_sync();
+          if (k == 0) {
+            stamp(it, 1);
+            const uint32_t acc = tmem_base + s * 256, a_addr = stage_addr(it), b_addr = sbase + kEfWe;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t koff = (ks >> 2) * kPanel + (ks & 3) * 32;
+              mma_ss(acc, sdesc_kmajor(a_addr + koff), sdesc_kmajor(b_addr + koff), idesc, ks != 0);
+            }
+            mma_commit(&bars[kEfAcc + s]);
+          } else {
+            stamp(it, 1 + k);
+            gemm_ts(s, k == 1 ? sbase + kEfW1 : sbase + kEfW2);
           }
-          mma_commit(&bars[kEfAcc + s]);
+          if (++slot_step[s] == 3) { slot_step[s] = 0; slot_tile[s] += 2; }
+          progressed = true;
         }
-        for (int s = 0; s < n; ++s) { wait_epi(s); gemm_ts(s, sbase + kEfW1); }
-        for (int s = 0; s < n; ++s) { wait_epi(s); gemm_ts(s, sbase + kEfW2); }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 24)) { debug_record(36, uint32_t(slot_tile[0]), uint32_t(slot_tile[1]), uint32_t(slot_step[0]), uint32_t(slot_step[1]), epi_phase[0], epi_phase[1]); __trap(); }
       }
     }
   } else {
@@ -210,7 +231,11 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
       }
       // ---- P0: H1 = relu(e We^T + Ps[s] + Pr[r] + b0) -> TMEM ------------------------------------------------
+      const int64_t srow = tile_row0(it) + r;              // my row; rows past the end compute on zero-filled input and store nothing
+      const bool stash = a.h1 != nullptr && srow < rows;
+      if ((tid & 255) == 0) stamp(it, 8);
       wait_acc(100);
+      if ((tid & 255) == 0) stamp(it, 9);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         uint32_t v[16], h[8];
@@ -229,12 +254,15 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           if (prrow != nullptr) ldg256_l1(prrow + 16 * (k + 2), pb[k & 1]);
         }
         tmem_st8(aop + k * 8, h);
+        if (stash) stg256_cs(a.h1 + srow * kD + hh * 64 + k * 16, h);
       }
       tmem_st_wait();
       fence_before_sync();
       mbar_arrive(&bars[kEfEpi + set]);
       // ---- P1: H2 = relu(H1 W1^T + b1) -> TMEM ------------------------------------------------------------------
+      if ((tid & 255) == 0) stamp(it, 10);
       wait_acc(101);
+      if ((tid & 255) == 0) stamp(it, 11);
 #pragma unroll
       for (int cg = 0; cg < 2; ++cg) {
         uint32_t v[32], h[16];
@@ -247,12 +275,15 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
         tmem_st8(aop + cg * 16, h);
         tmem_st8(aop + cg * 16 + 8, h + 8);
+        if (stash) { stg256_cs(a.h2 + srow * kD + hh * 64 + cg * 32, h); stg256_cs(a.h2 + srow * kD + hh * 64 + cg * 32 + 16, h + 8); }
       }
       tmem_st_wait();
       fence_before_sync();
       mbar_arrive(&bars[kEfEpi + set]);
       // ---- P2: y = H2 W2^T + b2 ; e' = e + LN(y) gamma + beta, written over e in the stage ------------------------------
+      if ((tid & 255) == 0) stamp(it, 12);
       wait_acc(102);
+      if ((tid & 255) == 0) stamp(it, 13);
       float2 y[32];
       {
         uint32_t v[32];
@@ -307,6 +338,7 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       }
       fence_async_smem();                                     // generic-proxy writes -> visible to the TMA store
       mbar_arrive(&bars[kEfOut + set]);
+      if ((tid & 255) == 0) stamp(it, 14);
     }
   }
   fence_before_sync();
@@ -339,7 +371,7 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows) {
 }
 
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
-                       const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st) {
+                       const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     uint32_t* dbg = debug_buffer_device();
@@ -358,11 +390,31 @@ int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, cons
   a.receivers = receivers;
   a.w0_chunks = w0_chunks;
   a.w0_chunk0 = w0_chunk0;
+  a.h1 = static_cast<__nv_bfloat16*>(h1);
+  a.h2 = static_cast<__nv_bfloat16*>(h1 != nullptr ? h2 : nullptr);
   const int64_t tiles = ceil_div(rows, kTile);
   const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
-  HGN_TIMED(name, st);
-  edge_fwd_tc_kernel<<<grid, kEfThreads, kEfSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a, tm_in, tm_out);
+  static long long* tl_dev = nullptr;
+  { const char* ab = getenv("HGN_TC_ABLATE"); if (ab != nullptr && (atoi(ab) & 64)) {
+      if (tl_dev == nullptr) cudaMalloc(&tl_dev, 12 * 32 * sizeof(long long));
+      cudaMemsetAsync(tl_dev, 0, 12 * 32 * sizeof(long long), st);
+      a.timeline = tl_dev;
+  } }
+  {
+    HGN_TIMED(name, st);
+    edge_fwd_tc_kernel<<<grid, kEfThreads, kEfSmem, st>>>(rows, tiles, static_cast<const uint8_t*>(packed), a, tm_in, tm_out);
+  }
   HGN_LAUNCH_OK(name);
+  if (a.timeline != nullptr) {
+    long long h[12 * 32];
+    cudaMemcpyAsync(h, a.timeline, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (int t = 0; t < 12; ++t) {
+      fprintf(stderr, "fwd tile %d:", t);
+      for (int k = 0; k < 24; ++k) fprintf(stderr, " %lld", h[t * 32 + k] ? h[t * 32 + k] - h[1] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return HGN_OK;
 }
 

@@ -751,6 +751,12 @@ __global__ void reduce_w0_block_kernel(const float* __restrict__ partial, int pa
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
+void launch_edge_bwd_reduce(const float* w_partial, const float* epi_colpart, const float* prod_colpart, int parts, int w0_chunks, int w0_chunk0,
+                            float* gW0, float* gW1, float* gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta, cudaStream_t st) {
+  edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi_colpart, prod_colpart, parts, w0_chunks, w0_chunk0, gW0,
+                                                                            gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
+}
+
 int tc_pair_wgrad(int64_t rows, const void* Ga, const void* Za, const void* Gb, const void* Zb, float* partial, int parts,
                   cudaStream_t st);                              // mlp_tc.cu
 int tc_pair_wgrad_parts(int64_t rows);
@@ -814,12 +820,18 @@ int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packe
 
 int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // edge_fwd_tc.cu
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
-                       const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st);   // edge_fwd_tc.cu
+                       const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name,
+                       cudaStream_t st);                                                                                  // edge_fwd_tc.cu
+int stash_backward_launch(int64_t rows, const void* dense, const void* h1, const void* h2, const int32_t* receivers, const void* packed,
+                          int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg, void* grad_dense, void* grad_pre0,
+                          float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
+                          float* w_partial, float* epi_colpart, float* prod_colpart, int grid, const char* name,
+                          cudaStream_t st);                                                                               // edge_bwd_stash_tc.cu
 
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st) {
+                           const int32_t* receivers, const void* packed, void* out, void* h1, void* h2, cudaStream_t st) {
   static const bool legacy = getenv("HGN_EDGE_FWD_LEGACY") != nullptr;     // development: the generic tile kernel with a pre-add
-  if (!legacy) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, "edge_fwd_tc", st);
+  if (!legacy || h1 != nullptr) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, h1, h2, "edge_fwd_tc", st);
   hgn_chunks ch{};
   ch.n_chunks = 1;
   ch.src[0] = edge;
@@ -910,11 +922,17 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
 }
 
 int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                            const int32_t* receivers, const void* packed, const void* grad_out, const void* grad_agg, void* grad_edge,
-                            void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
-                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                            const int32_t* receivers, const void* h1, const void* h2, const void* packed, const void* grad_out,
+                            const void* grad_agg, void* grad_edge, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
+                            float* gb2, float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const EdgeBwdLayout L = edge_bwd_layout(num_edges);
   if (workspace_bytes < L.total) { set_error("edge_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
+  if (h1 != nullptr && h2 != nullptr) {
+    char* ws = static_cast<char*>(workspace);
+    return stash_backward_launch(num_edges, edge, h1, h2, receivers, packed, 3, 2, grad_out, grad_agg, grad_edge, grad_pre0, gW0, gb0, gW1, gb1,
+                                 gW2, gb2, ggamma, gbeta, reinterpret_cast<float*>(ws + L.w_partial), reinterpret_cast<float*>(ws + L.epi),
+                                 reinterpret_cast<float*>(ws + L.prod), L.grid, "edge_bwd_stash_tc", st);
+  }
   return projected_backward_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, grad_out, grad_agg, grad_edge, grad_pre0,
                                    gW0, gb0, gW1, gb1, gW2, gb2, ggamma, gbeta, workspace, "edge_bwd_tc", st);
 }
@@ -922,13 +940,14 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
 // ---- node update in 'sum' mode through the same kernels (graphnet.py:34-48 with one aggregate) ---------------------------
 //   v' = v + LN(MLP([v | agg]))  with  W0 = [Wv | Wa]:  pre0 = Wv v + Q + b0,  Q = agg Wa^T  (one projection per node row, gathered
 //   through the identity), so the fused forward / backward kernels of the edge update serve the node update unchanged.
-int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, cudaStream_t st) {
+int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, void* h1, void* h2,
+                           cudaStream_t st) {
   LinArgs la{};
   la.in[0] = static_cast<const __nv_bfloat16*>(agg);
   la.out[0] = static_cast<__nv_bfloat16*>(q);
   la.n_in = 1; la.n_out = 1; la.b_mn = 0; la.w0_chunks = 2; la.chunk0 = 1;
   if (int rc = launch_proj(num_nodes, packed, la, "node_project_fwd", st)) return rc;
-  return edge_fwd_tc_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, out, "node_fwd_tc", st);
+  return edge_fwd_tc_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, out, h1, h2, "node_fwd_tc", st);
 }
 
 struct NodeBwdLayout { size_t edge, g0, partial, total; int parts; };
@@ -945,15 +964,24 @@ static NodeBwdLayout node_bwd_layout(int64_t n) {
 }
 size_t node_update_backward_workspace_tc(int64_t num_nodes) { return node_bwd_layout(num_nodes).total; }
 
-int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed, const void* grad_out,
+int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1, const void* h2,
+                            const void* packed, const void* grad_out,
                             void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
                             float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const NodeBwdLayout L = node_bwd_layout(num_nodes);
   if (workspace_bytes < L.total) { set_error("node_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
   char* ws = static_cast<char*>(workspace);
   void* g0 = ws + L.g0;
-  if (int rc = projected_backward_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1,
-                                         gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) return rc;
+  if (h1 != nullptr && h2 != nullptr) {
+    const EdgeBwdLayout E = edge_bwd_layout(num_nodes);
+    char* ews = ws + L.edge;
+    if (int rc = stash_backward_launch(num_nodes, v, h1, h2, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1, gW2, gb2,
+                                       ggamma, gbeta, reinterpret_cast<float*>(ews + E.w_partial), reinterpret_cast<float*>(ews + E.epi),
+                                       reinterpret_cast<float*>(ews + E.prod), E.grid, "node_bwd_stash_tc", st)) return rc;
+  } else if (int rc = projected_backward_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0,
+                                                gW1, gb1, gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) {
+    return rc;
+  }
   LinArgs la{};                                  // d agg = G0 Wa
   la.in[0] = static_cast<const __nv_bfloat16*>(g0);
   la.out[0] = static_cast<__nv_bfloat16*>(grad_agg);

@@ -49,12 +49,12 @@ SIGNATURES = {
     "hgn_edge_project_forward": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgn_edge_project_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hgn_edge_project_backward": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
-    "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p]),
+    "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_void_p]),
     "hgn_edge_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 18 + [c_void_p, c_size_t, c_void_p]),
-    "hgn_node_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 5 + [c_void_p]),
+    "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 20 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_node_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p]),
     "hgn_node_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_node_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 15 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_node_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 17 + [c_void_p, c_size_t, c_void_p]),
     "hgn_rows_gather": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -25,6 +25,20 @@ D_LATENT = 128
 OP_BITS = {"sum": AGG_SUM, "mean": AGG_MEAN, "max": AGG_MAX, "min": AGG_MIN}
 PNA_MASK = AGG_SUM | AGG_MEAN | AGG_MAX | AGG_MIN
 
+# Backward of the projected edge / node updates: 'recompute' (default) saves nothing but the block inputs; 'stash' keeps the
+# two hidden activations of the forward (2 x 256 B per row and layer) so that the backward skips the first two layers and the
+# table gathers.  On cfg5 the stash backward kernel is 0.9 ms faster per layer but the forward pays 0.6 ms for the extra
+# writes and the whole step ends up equal (both are then HBM-traffic bound) at +46 GB of HBM: see DESIGN.md s3.
+import os as _os
+backward_mode = _os.environ.get("HGN_B200_BACKWARD", "recompute")
+
+
+def _stash() -> bool:
+    if backward_mode not in ("stash", "recompute"):
+        raise _cabi.HgnError(f"unknown backward mode {backward_mode!r} (expected 'stash' or 'recompute')")
+    return backward_mode == "stash"
+
+
 # launch counter (bench.py reports "gpu_launches": kernels of ours launched in the timed region)
 launch_count = 0
 
@@ -333,10 +347,13 @@ class _EdgeUpdate(torch.autograd.Function):
         lib = _cabi.load()
         E = e.shape[0]
         out = torch.empty_like(e)
+        stash = _stash() and E > 0 and any(ctx.needs_input_grad)
+        h1 = torch.empty_like(e) if stash else None
+        h2 = torch.empty_like(e) if stash else None
         with torch.cuda.device(e.device):
             _cabi.check(lib.hgn_edge_update_forward(_cabi.HGN_BF16, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(),
-                                                    r_plan.ids32.data_ptr(), packed.data_ptr(), out.data_ptr(), _cabi.stream_ptr()),
-                        "hgn_edge_update_forward")
+                                                    r_plan.ids32.data_ptr(), packed.data_ptr(), out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2),
+                                                    _cabi.stream_ptr()), "hgn_edge_update_forward")
             _count()
             agg = None
             if want_agg:
@@ -345,7 +362,11 @@ class _EdgeUpdate(torch.autograd.Function):
                                                    r_plan.num_segments, agg.data_ptr(), None, None, None, None, None, 0, _cabi.stream_ptr()),
                             "hgn_segment_reduce")
                 _count()
-        ctx.save_for_backward(ps, pr, e)
+        if stash:
+            ctx.save_for_backward(e, h1, h2)        # the node tables are not needed again
+        else:
+            ctx.save_for_backward(e, ps, pr)
+        ctx.stash, ctx.n_nodes = stash, ps.shape[0]
         ctx.packed, ctx.s_plan, ctx.r_plan = packed, s_plan, r_plan
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         if want_agg:
@@ -355,10 +376,15 @@ class _EdgeUpdate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, grad_agg):
         lib = _cabi.load()
-        ps, pr, e = ctx.saved_tensors
+        if ctx.stash:
+            e, h1, h2 = ctx.saved_tensors
+            ps = pr = None
+        else:
+            e, ps, pr = ctx.saved_tensors
+            h1 = h2 = None
         s_plan, r_plan = ctx.s_plan, ctx.r_plan
         E, dev = e.shape[0], e.device
-        n = ps.shape[0]
+        n = ctx.n_nodes
         if grad_out is not None:
             grad_out = grad_out.contiguous().to(e.dtype)
         if grad_agg is not None:
@@ -373,8 +399,8 @@ class _EdgeUpdate(torch.autograd.Function):
             ws_bytes = lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_BF16, E)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.hgn_edge_update_backward(
-                _cabi.HGN_BF16, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
-                ctx.packed.data_ptr(), _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(),
+                _cabi.HGN_BF16, E, e.data_ptr(), _cabi.ptr(ps), _cabi.ptr(pr), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
+                _cabi.ptr(h1), _cabi.ptr(h2), ctx.packed.data_ptr(), _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(),
                 *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_edge_update_backward")
             _count(2)
             # d loss / d Ps, d Pr: sender- and receiver-keyed segment sums of G0 (deterministic CSR passes)
@@ -413,11 +439,18 @@ class _NodeUpdate(torch.autograd.Function):
         n = v.shape[0]
         q = torch.empty_like(v)
         out = torch.empty_like(v)
+        stash = _stash() and any(ctx.needs_input_grad)
+        h1 = torch.empty_like(v) if stash else None
+        h2 = torch.empty_like(v) if stash else None
         with torch.cuda.device(v.device):
             _cabi.check(lib.hgn_node_update_forward(_cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), packed.data_ptr(), q.data_ptr(),
-                                                    out.data_ptr(), _cabi.stream_ptr()), "hgn_node_update_forward")
+                                                    out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2), _cabi.stream_ptr()), "hgn_node_update_forward")
         _count(2)
-        ctx.save_for_backward(v, agg, q)
+        if stash:
+            ctx.save_for_backward(v, agg, h1, h2)
+        else:
+            ctx.save_for_backward(v, agg, q)
+        ctx.stash = stash
         ctx.packed = packed
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         return out
@@ -425,7 +458,12 @@ class _NodeUpdate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         lib = _cabi.load()
-        v, agg, q = ctx.saved_tensors
+        if ctx.stash:
+            v, agg, h1, h2 = ctx.saved_tensors
+            q = None
+        else:
+            v, agg, q = ctx.saved_tensors
+            h1 = h2 = None
         n, dev = v.shape[0], v.device
         grad_out = grad_out.contiguous().to(v.dtype)
         grad_v = torch.empty_like(v)
@@ -435,7 +473,7 @@ class _NodeUpdate(torch.autograd.Function):
             ws_bytes = lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.hgn_node_update_backward(
-                _cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), q.data_ptr(), ctx.packed.data_ptr(), grad_out.data_ptr(),
+                _cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), _cabi.ptr(q), _cabi.ptr(h1), _cabi.ptr(h2), ctx.packed.data_ptr(), grad_out.data_ptr(),
                 grad_v.data_ptr(), grad_agg.data_ptr(), *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
                 "hgn_node_update_backward")
         _count(5)

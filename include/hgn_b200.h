@@ -156,9 +156,12 @@ size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t num_nodes);
 int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed,
                               const void* grad_s, const void* grad_r, void* grad_v, float* grad_W0,
                               void* workspace, size_t workspace_bytes, void* stream);
+/* h1 / h2 (both or neither; bf16 [E,128], caller-owned) receive the two hidden activations relu(pre0) and
+ * relu(H1 W1^T + b1).  Handing them to the backward replaces its recomputation of the first two layers (and its
+ * gathers of the node tables) by two tile loads: a memory-for-time trade (2 x 256 B per edge). */
 int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
                             const int32_t* senders, const int32_t* receivers, const void* packed, void* out,
-                            void* stream);
+                            void* h1, void* h2, void* stream);
 /* Backward (activations recomputed).  The incoming gradient of e' is  grad_out[e] + grad_agg[receivers[e]] :
  * grad_out[E,128] (may be NULL) is the dense part (next layer / loss), grad_agg[N,128] (may be NULL) the gradient
  * of the 'sum' aggregate of e' over receivers (graphnet.py:50-70), gathered here instead of being expanded to
@@ -167,8 +170,9 @@ int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, cons
  * the inputs of hgn_edge_project_backward; grad_W0 columns 256:384 (= We) only; all other parameter gradients
  * complete (fp32, overwritten, fixed-order reductions). */
 size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges);
+/* With h1 / h2 from the forward (both non-NULL) proj_s, proj_r and senders are not read and may be NULL. */
 int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                             const int32_t* senders, const int32_t* receivers, const void* packed,
+                             const int32_t* senders, const int32_t* receivers, const void* h1, const void* h2, const void* packed,
                              const void* grad_out, const void* grad_agg, void* grad_edge, void* grad_pre0,
                              float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
@@ -181,9 +185,10 @@ int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, con
  * Backward (activations recomputed): grad_v = d loss / d v (residual branch included), grad_agg = d loss / d agg, and every
  * parameter gradient (fp32, overwritten, fixed-order reductions).  num_nodes must be > 0 for the backward. */
 int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed,
-                            void* q, void* out, void* stream);
+                            void* q, void* out, void* h1, void* h2, void* stream);   /* h1 / h2: optional stash, as above */
 size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes);
-int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* packed,
+int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q,
+                             const void* h1, const void* h2, const void* packed,
                              const void* grad_out, void* grad_v, void* grad_agg,
                              float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,

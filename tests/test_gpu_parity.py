@@ -280,11 +280,14 @@ def _bf16_emulated_projected_edge(v, e, s, r, w):
     return e + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
 
 
+@pytest.mark.parametrize("mode", ["stash", "recompute"])
 @pytest.mark.parametrize("want_agg", [False, True])
 @pytest.mark.parametrize("rows,n_nodes", [(1, 5), (63, 40), (128, 64), (129, 33), (1000, 300), (9282, 1600), (200000, 40000)])
-def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg):
+def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg, mode, monkeypatch):
     """ops.edge_update (node projection + fused edge forward/backward kernels with the aggregate's gradient gathered in
-    the kernel) against torch arithmetic with the same rounding points, on ragged tile counts."""
+    the kernel) against torch arithmetic with the same rounding points, on ragged tile counts, for both backward modes
+    (hidden activations stashed by the forward / recomputed)."""
+    monkeypatch.setattr(ops, "backward_mode", mode)
     torch.manual_seed(rows + int(want_agg))
     w = _random_mlp_weights(3, 11)
     params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
@@ -326,10 +329,12 @@ def _bf16_emulated_projected_node(v, agg, w):
     return v + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
 
 
+@pytest.mark.parametrize("mode", ["stash", "recompute"])
 @pytest.mark.parametrize("n_nodes", [1, 63, 128, 129, 1000, 1600, 40000])
-def test_projected_node_update_vs_bf16_emulation(n_nodes):
+def test_projected_node_update_vs_bf16_emulation(n_nodes, mode, monkeypatch):
     """ops.node_update (aggregate projection + the fused edge kernels driven with identity indices) against torch arithmetic
-    with the same rounding points, on ragged tile counts; run twice for bit determinism."""
+    with the same rounding points, on ragged tile counts; run twice for bit determinism; both backward modes."""
+    monkeypatch.setattr(ops, "backward_mode", mode)
     torch.manual_seed(n_nodes)
     w = _random_mlp_weights(2, 13)
     v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
@@ -355,7 +360,9 @@ def test_projected_node_update_vs_bf16_emulation(n_nodes):
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
 
-def test_projected_edge_update_is_deterministic():
+@pytest.mark.parametrize("mode", ["stash", "recompute"])
+def test_projected_edge_update_is_deterministic(mode, monkeypatch):
+    monkeypatch.setattr(ops, "backward_mode", mode)
     torch.manual_seed(3)
     w = _random_mlp_weights(3, 11)
     s = torch.randint(0, 3000, (20000,), device="cuda")
