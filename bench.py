@@ -255,12 +255,16 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
         "mlp_tile_tc_fwd": (n, F_NODE_SUM, F_NODE_SUM), "mlp_tile_tc_bwd": (n, F_NODE_SUM, 2 * F_NODE_SUM),
         "mlp_wgrad_tc": (n, F_NODE_SUM, F_NODE_SUM),
     }.get(top["name"])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at the full cfg5 size, from the ncu --set full capture in
+    # profiles/r1_final_ncu_full_edge_kernels.txt (only meaningful for the single-GPU cfg5 launch sizes)
+    ncu_traffic = {"edge_bwd_tc": 4.699e9 + 3.050e9, "edge_fwd_tc": 2.609e9 + 1.501e9, "segment_reduce": 1.562e9 + 0.247e9}
+    traffic = ncu_traffic.get(top["name"]) if e == 5992002 else None
     if tensor is not None:
         rows, algo_row, exec_row = tensor
         achieved = rows * algo_row / (mean_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         return {"kernel": top["name"], "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "mean_launch_ms": mean_ms, "launches_per_step": top["launches"] / steps,
+                "traffic": traffic, "mean_launch_ms": mean_ms, "launches_per_step": top["launches"] / steps,
                 "algorithmic_flops_per_launch": rows * algo_row, "executed_tflops": rows * exec_row / (mean_ms * 1e-3) / 1e12,
                 "share_of_step": top["ms"] / sum(k["ms"] for k in kernels),
                 "peak_source": peaks["source"] + ", sustained bf16"}
@@ -269,7 +273,7 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
                     "multi_segment_sum": (2 * e + n) * 256 + 2 * e * 4, "colsum": e * 256}.get(top["name"], 0)
     achieved = bytes_launch / (mean_ms * 1e-3) / 1e9
     return {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "mean_launch_ms": mean_ms,
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "mean_launch_ms": mean_ms,
             "share_of_step": top["ms"] / sum(k["ms"] for k in kernels), "peak_source": peaks["source"]}
 
 
