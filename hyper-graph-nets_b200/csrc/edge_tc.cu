@@ -216,13 +216,13 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       mbar_init(&bars[kEbFull], 1);                           // one arrive.expect_tx per tile, completed by the TMA bytes
       mbar_init(&bars[kEbWg], 1);
       mbar_init(&bars[kEbFinal], 1);
-      mbar_init(&bars[kEbDe], kEbEpiThreads);
+      mbar_init(&bars[kEbDe], kEbEpiThreads / 32);            // epilogue barriers: one arrival per WARP (lane 0 after __syncwarp):
       mbar_init(&bars[kEbDeFree], 1);
       mbar_init(&bars[kEbG0Free], 1);
       mbar_init(&bars[kEbAcc], 1);
-      mbar_init(&bars[kEbEpi], kEbEpiThreads);
-      mbar_init(&bars[kEbAfree], kEbEpiThreads);
-      for (int k = 0; k < 3; ++k) { mbar_init(&bars[kEbG + k], kEbEpiThreads); mbar_init(&bars[kEbCs + k], kEbProdThreads); }
+      mbar_init(&bars[kEbEpi], kEbEpiThreads / 32);           // 256 arrivals on one mbarrier serialise in the shared-memory unit
+      mbar_init(&bars[kEbAfree], kEbEpiThreads / 32);
+      for (int k = 0; k < 3; ++k) { mbar_init(&bars[kEbG + k], kEbEpiThreads / 32); mbar_init(&bars[kEbCs + k], kEbProdThreads / 32); }
       mbar_init_fence();
     }
     if (warp == 10) tmem_alloc<512>(reinterpret_cast<uint32_t*>(&bars[kEbTmem]));
@@ -300,10 +300,10 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       }
       mbar_wait(&bars[kEbG + 0], par, 50);
       colsum(buf(3, t), cs[0]);                              // dY
-      mbar_arrive(&bars[kEbCs + 0]);
+      __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbCs + 0]);
       mbar_wait(&bars[kEbG + 1], par, 51);
       colsum(buf(2, t), cs[1]);                              // dH2'
-      mbar_arrive(&bars[kEbCs + 1]);
+      __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbCs + 1]);
       mbar_wait(&bars[kEbAfree], par, 52);                   // H1 has been read back and the dW1 MMAs are done:
       if (more) load_e(t + 1);                               // buffer A(t) = S(t+1) takes the next tile's edge rows
       mbar_wait(&bars[kEbG + 2], par, 53);                   // dH1' = G0 is in buffer C (and fenced for the async proxy)
@@ -315,7 +315,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       }
       colsum(buf(3, t), cs[2]);
       if (ptid == 0) tma_store_wait_read<0>();               // the store has read the buffer before E1 of the next tile reuses it
-      mbar_arrive(&bars[kEbCs + 2]);
+      __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbCs + 2]);
     }
     if (ptid == 0) tma_store_wait<0>();
 #pragma unroll
@@ -401,8 +401,11 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     auto done = [&](int producers_k) {   // producers_k >= 0: the tile just written is also the producers' column-sum input k
       fence_async_smem();          // generic-proxy tile writes -> visible to the tensor core's async-proxy reads
       fence_before_sync();
-      mbar_arrive(&bars[kEbEpi]);
-      if (producers_k >= 0) mbar_arrive(&bars[kEbG + producers_k]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars[kEbEpi]);
+        if (producers_k >= 0) mbar_arrive(&bars[kEbG + producers_k]);
+      }
     };
     const uint32_t row_off = hh * kPanel;                      // my 64 columns = panel hh of every buffer
     auto store_row = [&](uint32_t bufaddr, const uint32_t* w) {   // 64 columns (32 packed words) of row r
@@ -625,7 +628,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         wait_acc(104); if (tid == 0) stamp(a, t, 18);
         uint32_t hw[32], o[32];
         load_row(A, hw);                                        // H1: the last reader of buffer A in this tile
-        mbar_arrive(&bars[kEbAfree]);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbAfree]);
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
           uint32_t v[32];
@@ -653,7 +656,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         // the accumulator is in registers: the next tile's step 0 may overwrite it while this phase does its arithmetic and
         // stores (no shared-memory writes here, so no proxy fence)
         fence_before_sync();
-        mbar_arrive(&bars[kEbEpi]);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbEpi]);
         uint32_t o[32];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -665,7 +668,7 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         // staged in buffer B (dH2' is dead: the chain commit above came after the dW1 MMAs) and stored by the producers' TMA
         store_row(B, o);
         fence_async_smem();
-        mbar_arrive(&bars[kEbDe]);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbDe]);
         if (tid == 0) {                                         // one thread stores the staged tile once all 256 rows are in
           mbar_wait(&bars[kEbDe], uint32_t(t) & 1, 77);
           if (!(a.ablate & 2)) {

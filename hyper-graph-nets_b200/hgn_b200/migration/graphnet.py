@@ -134,7 +134,10 @@ class GraphNet(nn.Module):
             # throughput mode, one aggregate: the aggregate's block of the first linear is applied per node row and the
             # projected edge kernels do the rest (ops._NodeUpdate).  With hyper / ghost rows in the list only the target's
             # slice of the aggregate is consumed, like the reference's agg_features[:N] / [N:] (graphnet.py:45,105).
-            return ops.node_update(params, _packed_cache(model), node_features[target], aggregates[0][offset: offset + rows])
+            agg = aggregates[0]
+            if offset != 0 or rows != agg.shape[0]:       # a full-range slice would still cost a zero-fill + copy in backward
+                agg = agg[offset: offset + rows]
+            return ops.node_update(params, _packed_cache(model), node_features[target], agg)
         chunks = [ops.ChunkSpec(i, None, offset) for i in range(len(sources))]
         return ops.fused_mlp(params, _packed_cache(model), sources, chunks, rows=rows, resid_source=0, resid_offset=offset)
 
