@@ -104,7 +104,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------------
-def build_inputs(width, height, layers, seed=0):
+def build_inputs(width, height, layers, seed=0, aggregator="sum"):
     """Host-side (pinned) latents, int64 edge lists and the seeded processor weights."""
     from hgn_b200 import synthetic
     senders, receivers = synthetic.grid_edges_two_way(width, height)
@@ -113,13 +113,13 @@ def build_inputs(width, height, layers, seed=0):
     v0 = torch.randn(n, LATENT, generator=gen)
     e0 = torch.randn(e, LATENT, generator=gen)
     coef_v = torch.randn(n, LATENT, generator=gen)
-    weights = synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), seed=17)
+    weights = synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], aggregator), seed=17)
     return {"senders": senders, "receivers": receivers, "v0": v0, "e0": e0, "coef_v": coef_v, "weights": weights, "n": n, "e": e}
 
 
-def make_processor(weights, layers, precision, device):
+def make_processor(weights, layers, precision, device, aggregator="sum"):
     from hgn_b200.migration.meshgraphnet import MeshGraphNet
-    shell = MeshGraphNet(3, LATENT, 2, "sum", layers, "none", ["mesh_edges"])
+    shell = MeshGraphNet(3, LATENT, 2, aggregator, layers, "none", ["mesh_edges"])
     proc = shell.processor
     proc.load_state_dict({k[len("processor."):]: t for k, t in weights.items()})
     proc = proc.to(device)
@@ -143,9 +143,9 @@ def run_ours(args):
         return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler,
                                            dominant_kernel_roofline)
 
-    data = build_inputs(GRID_W, GRID_H, LAYERS)
+    data = build_inputs(GRID_W, GRID_H, LAYERS, aggregator=args.aggregator)
     n, e = data["n"], data["e"]
-    proc = make_processor(data["weights"], LAYERS, "bf16", dev)
+    proc = make_processor(data["weights"], LAYERS, "bf16", dev, args.aggregator)
     params = [p for p in proc.parameters()]
     senders, receivers = data["senders"].to(dev), data["receivers"].to(dev)
     v0_host, e0_host = data["v0"].pin_memory(), data["e0"].pin_memory()
@@ -220,7 +220,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
-        "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, "
+        "config": {"workload": f"cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, {args.aggregator} aggregator, "
                                "processor fwd+bwd", "nodes": n, "edges": e, "layers": LAYERS, "latent": LATENT,
                    "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none",
                    "backward": ops.backward_mode},
@@ -350,6 +350,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--aggregator", default="sum", choices=["sum", "pna"],
+                    help="message-passing aggregator (the headline metric is quoted on 'sum'; 'pna' is the reference configs' default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

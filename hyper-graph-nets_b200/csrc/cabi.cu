@@ -96,13 +96,13 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
                             const void* grad_agg, void* grad_edge, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
                             float* gb2, float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, void* h1, void* h2,
-                           cudaStream_t st);
+int node_update_forward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* packed, void* q1, void* q2,
+                           void* out, void* h1, void* h2, cudaStream_t st);
 size_t node_update_backward_workspace_tc(int64_t num_nodes);
-int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1, const void* h2,
-                            const void* packed, const void* grad_out,
-                            void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
-                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* q1, const void* q2,
+                            const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
+                            float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
+                            void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 static int check_chunks(const hgn_chunks* ch, const char* who) {
   HGN_CHECK_ARG(ch != nullptr, "%s: chunks is NULL", who);
@@ -248,14 +248,16 @@ extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void
                                  static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out,
-                                       void* h1, void* h2, void* stream) {
+extern "C" int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* packed,
+                                       void* q1, void* q2, void* out, void* h1, void* h2, void* stream) {
   HGN_BF16_ONLY("node_update_forward");
   HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "node_update_forward: num_nodes=%lld", (long long)num_nodes);
+  HGN_CHECK_ARG(n_agg >= 1 && n_agg <= 4 && aggs != nullptr, "node_update_forward: n_agg=%d outside [1,4]", n_agg);
   if (num_nodes == 0) return HGN_OK;
-  HGN_CHECK_ARG(v && agg && packed && q && out, "node_update_forward: null pointer");
+  for (int j = 0; j < n_agg; ++j) HGN_CHECK_ARG(aggs[j] != nullptr, "node_update_forward: aggregate %d is NULL", j);
+  HGN_CHECK_ARG(v && packed && q1 && out && (n_agg <= 2 || q2), "node_update_forward: null pointer");
   HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "node_update_forward: h1 and h2 must be given together");
-  return node_update_forward_tc(num_nodes, v, agg, packed, q, out, h1, h2, static_cast<cudaStream_t>(stream));
+  return node_update_forward_tc(num_nodes, v, n_agg, aggs, packed, q1, q2, out, h1, h2, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes) {
@@ -263,18 +265,21 @@ extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t nu
   return node_update_backward_workspace_tc(num_nodes);
 }
 
-extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1,
-                                        const void* h2, const void* packed,
-                                        const void* grad_out, void* grad_v, void* grad_agg, float* grad_W0, float* grad_b0, float* grad_W1,
-                                        float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* q1,
+                                        const void* q2, const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v,
+                                        void* const* grad_aggs, float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1, float* grad_W2,
+                                        float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
   HGN_BF16_ONLY("node_update_backward");
   HGN_CHECK_ARG(num_nodes > 0 && num_nodes < (int64_t(1) << 31), "node_update_backward: num_nodes=%lld", (long long)num_nodes);
-  HGN_CHECK_ARG(v && agg && packed && grad_out && grad_v && grad_agg && workspace, "node_update_backward: null pointer");
-  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr) && (h1 || q), "node_update_backward: needs q (recompute) or h1 and h2 (stash)");
+  HGN_CHECK_ARG(n_agg >= 1 && n_agg <= 4 && aggs != nullptr && grad_aggs != nullptr, "node_update_backward: n_agg=%d outside [1,4]", n_agg);
+  for (int j = 0; j < n_agg; ++j) HGN_CHECK_ARG(aggs[j] != nullptr && grad_aggs[j] != nullptr, "node_update_backward: aggregate %d is NULL", j);
+  HGN_CHECK_ARG(v && packed && grad_out && grad_v && workspace, "node_update_backward: null pointer");
+  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr) && (h1 || (q1 && (n_agg <= 2 || q2))),
+                "node_update_backward: needs the q tables (recompute) or h1 and h2 (stash)");
   HGN_CHECK_ARG(grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta, "node_update_backward: null pointer");
-  return node_update_backward_tc(num_nodes, v, agg, q, h1, h2, packed, grad_out, grad_v, grad_agg, grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2,
-                                 grad_gamma, grad_beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return node_update_backward_tc(num_nodes, v, n_agg, aggs, q1, q2, h1, h2, packed, grad_out, grad_v, grad_aggs, grad_W0, grad_b0, grad_W1,
+                                 grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hgn_profile_enable(int on) { g_profile_on = on != 0; return HGN_OK; }

@@ -943,14 +943,20 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
 // ---- node update in 'sum' mode through the same kernels (graphnet.py:34-48 with one aggregate) ---------------------------
 //   v' = v + LN(MLP([v | agg]))  with  W0 = [Wv | Wa]:  pre0 = Wv v + Q + b0,  Q = agg Wa^T  (one projection per node row, gathered
 //   through the identity), so the fused forward / backward kernels of the edge update serve the node update unchanged.
-int node_update_forward_tc(int64_t num_nodes, const void* v, const void* agg, const void* packed, void* q, void* out, void* h1, void* h2,
-                           cudaStream_t st) {
-  LinArgs la{};
-  la.in[0] = static_cast<const __nv_bfloat16*>(agg);
-  la.out[0] = static_cast<__nv_bfloat16*>(q);
-  la.n_in = 1; la.n_out = 1; la.b_mn = 0; la.w0_chunks = 2; la.chunk0 = 1;
-  if (int rc = launch_proj(num_nodes, packed, la, "node_project_fwd", st)) return rc;
-  return edge_fwd_tc_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, out, h1, h2, "node_fwd_tc", st);
+// n_agg = 1..4 aggregates (one 'sum', or sum/mean/max/min of 'pna'): W0 = [Wv | Wa_1 | ... | Wa_n].  The aggregates' blocks of the
+// first linear are applied per node row into at most two tables, q1 = agg_1 Wa_1^T (+ agg_2 Wa_2^T) and q2 = agg_3 Wa_3^T (+ agg_4
+// Wa_4^T), which the fused kernel gathers through the identity in the places of Ps[s] and Pr[r].
+int node_update_forward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* packed, void* q1, void* q2,
+                           void* out, void* h1, void* h2, cudaStream_t st) {
+  for (int t = 0; t * 2 < n_agg; ++t) {
+    LinArgs la{};
+    la.n_in = n_agg - 2 * t >= 2 ? 2 : 1;
+    for (int c = 0; c < la.n_in; ++c) la.in[c] = static_cast<const __nv_bfloat16*>(aggs[2 * t + c]);
+    la.out[0] = static_cast<__nv_bfloat16*>(t == 0 ? q1 : q2);
+    la.n_out = 1; la.b_mn = 0; la.w0_chunks = 1 + n_agg; la.chunk0 = 1 + 2 * t;
+    if (int rc = launch_proj(num_nodes, packed, la, "node_project_fwd", st)) return rc;
+  }
+  return edge_fwd_tc_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, 1 + n_agg, 0, out, h1, h2, "node_fwd_tc", st);
 }
 
 struct NodeBwdLayout { size_t edge, g0, partial, total; int parts; };
@@ -967,36 +973,42 @@ static NodeBwdLayout node_bwd_layout(int64_t n) {
 }
 size_t node_update_backward_workspace_tc(int64_t num_nodes) { return node_bwd_layout(num_nodes).total; }
 
-int node_update_backward_tc(int64_t num_nodes, const void* v, const void* agg, const void* q, const void* h1, const void* h2,
-                            const void* packed, const void* grad_out,
-                            void* grad_v, void* grad_agg, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma,
-                            float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* q1, const void* q2,
+                            const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
+                            float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
+                            void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const NodeBwdLayout L = node_bwd_layout(num_nodes);
   if (workspace_bytes < L.total) { set_error("node_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
   char* ws = static_cast<char*>(workspace);
   void* g0 = ws + L.g0;
+  const int w0_chunks = 1 + n_agg;
   if (h1 != nullptr && h2 != nullptr) {
     const EdgeBwdLayout E = edge_bwd_layout(num_nodes);
     char* ews = ws + L.edge;
-    if (int rc = stash_backward_launch(num_nodes, v, h1, h2, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1, gW2, gb2,
-                                       ggamma, gbeta, reinterpret_cast<float*>(ews + E.w_partial), reinterpret_cast<float*>(ews + E.epi),
+    if (int rc = stash_backward_launch(num_nodes, v, h1, h2, nullptr, packed, w0_chunks, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1, gW2,
+                                       gb2, ggamma, gbeta, reinterpret_cast<float*>(ews + E.w_partial), reinterpret_cast<float*>(ews + E.epi),
                                        reinterpret_cast<float*>(ews + E.prod), E.grid, "node_bwd_stash_tc", st)) return rc;
-  } else if (int rc = projected_backward_launch(num_nodes, v, q, nullptr, nullptr, nullptr, packed, 2, 0, grad_out, nullptr, grad_v, g0, gW0, gb0,
-                                                gW1, gb1, gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) {
+  } else if (int rc = projected_backward_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, w0_chunks, 0, grad_out, nullptr,
+                                                grad_v, g0, gW0, gb0, gW1, gb1, gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) {
     return rc;
   }
-  LinArgs la{};                                  // d agg = G0 Wa
-  la.in[0] = static_cast<const __nv_bfloat16*>(g0);
-  la.out[0] = static_cast<__nv_bfloat16*>(grad_agg);
-  la.n_in = 1; la.n_out = 1; la.b_mn = 1; la.w0_chunks = 2; la.chunk0 = 1;
-  if (int rc = launch_proj(num_nodes, packed, la, "node_project_dgrad", st)) return rc;
-  float* partial = reinterpret_cast<float*>(ws + L.partial);     // d Wa = G0^T agg
-  if (int rc = tc_pair_wgrad(num_nodes, g0, agg, nullptr, nullptr, partial, L.parts, st)) return rc;
-  {
-    HGN_TIMED("reduce_weight_partials", st);
-    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 1, gW0, 2 * kD, kD);
+  float* partial = reinterpret_cast<float*>(ws + L.partial);
+  for (int t = 0; t * 2 < n_agg; ++t) {
+    const int n = n_agg - 2 * t >= 2 ? 2 : 1;
+    LinArgs la{};                                // d agg_j = G0 Wa_j for the (up to) two aggregates of table t
+    la.in[0] = static_cast<const __nv_bfloat16*>(g0);
+    for (int o = 0; o < n; ++o) la.out[o] = static_cast<__nv_bfloat16*>(grad_aggs[2 * t + o]);
+    la.n_in = 1; la.n_out = n; la.b_mn = 1; la.w0_chunks = w0_chunks; la.chunk0 = 1 + 2 * t;
+    if (int rc = launch_proj(num_nodes, packed, la, "node_project_dgrad", st)) return rc;
+    // d Wa_j = G0^T agg_j  (pair kernel: partial z = 1 holds the first pair, z = 0 the second)
+    if (int rc = tc_pair_wgrad(num_nodes, g0, aggs[2 * t], n == 2 ? g0 : nullptr, n == 2 ? aggs[2 * t + 1] : nullptr, partial, L.parts, st)) return rc;
+    {
+      HGN_TIMED("reduce_weight_partials", st);
+      reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 1, gW0, w0_chunks * kD, (1 + 2 * t) * kD);
+      if (n == 2) reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 0, gW0, w0_chunks * kD, (2 + 2 * t) * kD);
+    }
+    HGN_LAUNCH_OK("node_update_backward reductions");
   }
-  HGN_LAUNCH_OK("node_update_backward reductions");
   return HGN_OK;
 }
 

@@ -52,9 +52,9 @@ SIGNATURES = {
     "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_void_p]),
     "hgn_edge_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 20 + [c_void_p, c_size_t, c_void_p]),
-    "hgn_node_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p]),
+    "hgn_node_update_forward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 6 + [c_void_p]),
     "hgn_node_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_node_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 17 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_node_update_backward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 7 + [POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "hgn_rows_gather": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -129,15 +129,15 @@ class GraphNet(nn.Module):
         aggregates = self._aggregates(edge_sets, v.shape[0], v.device)
         sources = [v] + aggregates
         params = _mlp_parameters(model, v.shape[1] * len(sources), v)
-        if (len(aggregates) == 1 and rows > 0 and v.dtype == torch.bfloat16 and aggregates[0].dtype == torch.bfloat16
-                and v.shape[1] == ops.D_LATENT):
-            # throughput mode, one aggregate: the aggregate's block of the first linear is applied per node row and the
-            # projected edge kernels do the rest (ops._NodeUpdate).  With hyper / ghost rows in the list only the target's
-            # slice of the aggregate is consumed, like the reference's agg_features[:N] / [N:] (graphnet.py:45,105).
-            agg = aggregates[0]
-            if offset != 0 or rows != agg.shape[0]:       # a full-range slice would still cost a zero-fill + copy in backward
-                agg = agg[offset: offset + rows]
-            return ops.node_update(params, _packed_cache(model), node_features[target], agg)
+        if (1 <= len(aggregates) <= 4 and rows > 0 and v.dtype == torch.bfloat16
+                and all(a.dtype == torch.bfloat16 for a in aggregates) and v.shape[1] == ops.D_LATENT):
+            # throughput mode, one edge set ('sum' ... or the four 'pna' aggregates): the aggregates' blocks of the first linear
+            # are applied per node row and the projected edge kernels do the rest (ops._NodeUpdate).  With hyper / ghost rows in
+            # the list only the target's slice of each aggregate is consumed, like the reference's agg_features[:N] / [N:]
+            # (graphnet.py:45,105); a full-range slice is skipped (it would still cost a zero-fill + copy in backward).
+            full = offset == 0 and rows == aggregates[0].shape[0]
+            aggs = aggregates if full else [a[offset: offset + rows] for a in aggregates]
+            return ops.node_update(params, _packed_cache(model), node_features[target], aggs)
         chunks = [ops.ChunkSpec(i, None, offset) for i in range(len(sources))]
         return ops.fused_mlp(params, _packed_cache(model), sources, chunks, rows=rows, resid_source=0, resid_offset=offset)
 

@@ -430,27 +430,31 @@ def edge_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Ten
 
 
 class _NodeUpdate(torch.autograd.Function):
-    """``v' = v + LN(MLP([v | agg]))`` (graphnet.py:34-48 with one 'sum' aggregate) on the projected kernels: the aggregate's
-    block of the first linear is applied once per node row (``q = agg Wa^T``) and enters the fused kernel as a table row."""
+    """``v' = v + LN(MLP([v | agg_1 | ... | agg_n]))`` (graphnet.py:34-48, one edge set: n = 1, or 4 for 'pna') on the projected
+    kernels: the aggregates' blocks of the first linear are applied once per node row into one or two tables
+    (``q1 = agg_1 Wa_1^T + agg_2 Wa_2^T``, ``q2 = agg_3 Wa_3^T + agg_4 Wa_4^T``) that enter the fused kernel as table rows."""
 
     @staticmethod
-    def forward(ctx, v, agg, W0, b0, W1, b1, W2, b2, gamma, beta, packed):
+    def forward(ctx, v, W0, b0, W1, b1, W2, b2, gamma, beta, packed, *aggs):
         lib = _cabi.load()
-        n = v.shape[0]
-        q = torch.empty_like(v)
+        n, k = v.shape[0], len(aggs)
+        q1 = torch.empty_like(v)
+        q2 = torch.empty_like(v) if k > 2 else None
         out = torch.empty_like(v)
         stash = _stash() and any(ctx.needs_input_grad)
         h1 = torch.empty_like(v) if stash else None
         h2 = torch.empty_like(v) if stash else None
+        agg_ptrs = (ctypes.c_void_p * k)(*[a.data_ptr() for a in aggs])
         with torch.cuda.device(v.device):
-            _cabi.check(lib.hgn_node_update_forward(_cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), packed.data_ptr(), q.data_ptr(),
-                                                    out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2), _cabi.stream_ptr()), "hgn_node_update_forward")
-        _count(2)
+            _cabi.check(lib.hgn_node_update_forward(_cabi.HGN_BF16, n, v.data_ptr(), k, agg_ptrs, packed.data_ptr(), q1.data_ptr(),
+                                                    _cabi.ptr(q2), out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2), _cabi.stream_ptr()),
+                        "hgn_node_update_forward")
+        _count(1 + (k + 1) // 2)
         if stash:
-            ctx.save_for_backward(v, agg, h1, h2)
+            ctx.save_for_backward(v, *aggs, h1, h2)
         else:
-            ctx.save_for_backward(v, agg, q)
-        ctx.stash = stash
+            ctx.save_for_backward(v, *aggs, q1, *([q2] if q2 is not None else []))
+        ctx.stash, ctx.k = stash, k
         ctx.packed = packed
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         return out
@@ -458,40 +462,52 @@ class _NodeUpdate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         lib = _cabi.load()
+        saved = list(ctx.saved_tensors)
+        k = ctx.k
+        v, aggs, rest = saved[0], saved[1:1 + k], saved[1 + k:]
         if ctx.stash:
-            v, agg, h1, h2 = ctx.saved_tensors
-            q = None
+            h1, h2 = rest
+            q1 = q2 = None
         else:
-            v, agg, q = ctx.saved_tensors
             h1 = h2 = None
+            q1 = rest[0]
+            q2 = rest[1] if len(rest) > 1 else None
         n, dev = v.shape[0], v.device
         grad_out = grad_out.contiguous().to(v.dtype)
         grad_v = torch.empty_like(v)
-        grad_agg = torch.empty_like(agg)
+        grad_aggs = [torch.empty_like(a) for a in aggs]
         gparams = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes]
+        agg_ptrs = (ctypes.c_void_p * k)(*[a.data_ptr() for a in aggs])
+        gagg_ptrs = (ctypes.c_void_p * k)(*[g.data_ptr() for g in grad_aggs])
         with torch.cuda.device(dev):
             ws_bytes = lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.hgn_node_update_backward(
-                _cabi.HGN_BF16, n, v.data_ptr(), agg.data_ptr(), _cabi.ptr(q), _cabi.ptr(h1), _cabi.ptr(h2), ctx.packed.data_ptr(), grad_out.data_ptr(),
-                grad_v.data_ptr(), grad_agg.data_ptr(), *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
-                "hgn_node_update_backward")
-        _count(5)
-        return (grad_v, grad_agg, *gparams, None)
+                _cabi.HGN_BF16, n, v.data_ptr(), k, agg_ptrs, _cabi.ptr(q1), _cabi.ptr(q2), _cabi.ptr(h1), _cabi.ptr(h2),
+                ctx.packed.data_ptr(), grad_out.data_ptr(), grad_v.data_ptr(), gagg_ptrs, *[g.data_ptr() for g in gparams],
+                ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_node_update_backward")
+        _count(2 + 3 * ((k + 1) // 2))
+        return (grad_v, *gparams, None, *grad_aggs)
 
 
-def node_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Tensor, agg: torch.Tensor) -> torch.Tensor:
-    """Projected bf16 node update with a single aggregate: ``v + LN(MLP([v | agg]))``."""
-    _cabi.require_cuda(v, agg)
-    if v.dtype != torch.bfloat16 or agg.dtype != torch.bfloat16:
+def node_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Tensor, aggs) -> torch.Tensor:
+    """Projected bf16 node update ``v + LN(MLP([v | agg_1 | ... | agg_n]))`` with 1 to 4 aggregates (one tensor or a sequence)."""
+    if isinstance(aggs, torch.Tensor):
+        aggs = [aggs]
+    aggs = list(aggs)
+    _cabi.require_cuda(v, *aggs)
+    if v.dtype != torch.bfloat16 or any(a.dtype != torch.bfloat16 for a in aggs):
         raise _cabi.HgnError("node_update is the bf16 tcgen05 path; fp32 features go through fused_mlp")
-    W0 = params[0]
-    if W0.shape != (D_LATENT, 2 * D_LATENT) or v.shape != agg.shape or v.shape[-1] != D_LATENT or v.shape[0] == 0:
-        raise _cabi.HgnError(f"node_update is specialised for latent 128 and one aggregate: W0 {tuple(W0.shape)}, v {tuple(v.shape)}")
-    v, agg = v.contiguous(), agg.contiguous()
+    W0, k = params[0], len(aggs)
+    if (not 1 <= k <= 4 or W0.shape != (D_LATENT, (1 + k) * D_LATENT) or any(a.shape != v.shape for a in aggs)
+            or v.shape[-1] != D_LATENT or v.shape[0] == 0):
+        raise _cabi.HgnError(f"node_update is specialised for latent 128 and 1..4 aggregates: W0 {tuple(W0.shape)}, v {tuple(v.shape)}, "
+                             f"{k} aggregates")
+    v = v.contiguous()
+    aggs = [a.contiguous() for a in aggs]
     with torch.cuda.device(v.device):
-        packed = _pack_weights(packed_cache, torch.bfloat16, 2, params)
-    return _NodeUpdate.apply(v, agg, *params, packed)
+        packed = _pack_weights(packed_cache, torch.bfloat16, 1 + k, params)
+    return _NodeUpdate.apply(v, *params, packed, *aggs)
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:

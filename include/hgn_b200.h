@@ -178,18 +178,20 @@ int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, con
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
                              void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- node update, one 'sum' aggregate (HGN_BF16 only) -- src/migration/graphnet.py:34-48 with S = 1, k = 1 -------------
- *     v' = v + LN(W2 relu(W1 relu(Wv v + Wa agg + b0) + b1) + b2),   W0 = [Wv | Wa] = node_model_cross.0.layers.linear_0.weight
- * `packed` is the hgn_mlp_pack blob of the node MLP with n_chunks = 2.  q[N,128] (caller-owned, bf16) receives agg Wa^T, which the
- * backward reads again.  Runs on the projected edge kernels: q plays the role of a node table gathered through the identity.
- * Backward (activations recomputed): grad_v = d loss / d v (residual branch included), grad_agg = d loss / d agg, and every
- * parameter gradient (fp32, overwritten, fixed-order reductions).  num_nodes must be > 0 for the backward. */
-int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* packed,
-                            void* q, void* out, void* h1, void* h2, void* stream);   /* h1 / h2: optional stash, as above */
+/* ---- node update with 1..4 aggregates (HGN_BF16 only) -- src/migration/graphnet.py:34-48 with one edge set -----------------
+ *     v' = v + LN(W2 relu(W1 relu(Wv v + sum_j Wa_j agg_j + b0) + b1) + b2),   W0 = [Wv | Wa_1 | ... | Wa_n] = node_model_cross.0.layers.linear_0.weight
+ * n_agg = 1 ('sum', 'mean', 'max' or 'min') or 4 ('pna': sum, mean, max, min in the order of graphnet.py:53-64); aggs[j] is [N,128] bf16.
+ * `packed` is the hgn_mlp_pack blob of the node MLP with n_chunks = 1 + n_agg.  q1 (and q2 when n_agg > 2; caller-owned [N,128] bf16)
+ * receive agg_1 Wa_1^T + agg_2 Wa_2^T and agg_3 Wa_3^T + agg_4 Wa_4^T; the recompute backward reads them again.  Runs on the projected
+ * edge kernels: the q tables play the roles of the node tables, gathered through the identity.  h1 / h2: optional stash, as above.
+ * Backward: grad_v = d loss / d v (residual branch included), grad_aggs[j] = d loss / d agg_j, and every parameter gradient (fp32,
+ * overwritten, fixed-order reductions).  num_nodes must be > 0 for the backward. */
+int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* packed,
+                            void* q1, void* q2, void* out, void* h1, void* h2, void* stream);
 size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes);
-int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, const void* agg, const void* q,
-                             const void* h1, const void* h2, const void* packed,
-                             const void* grad_out, void* grad_v, void* grad_agg,
+int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs,
+                             const void* q1, const void* q2, const void* h1, const void* h2, const void* packed,
+                             const void* grad_out, void* grad_v, void* const* grad_aggs,
                              float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
                              void* workspace, size_t workspace_bytes, void* stream);

@@ -319,43 +319,53 @@ def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg, mode, 
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
 
-def _bf16_emulated_projected_node(v, agg, w):
-    """Rounding points of ops.node_update: bf16 operands, bf16 q = agg Wa^T table, bf16 H1/H2."""
+def _bf16_emulated_projected_node(v, aggs, w):
+    """Rounding points of ops.node_update: bf16 operands, bf16 tables q1 = agg_1 Wa_1^T + agg_2 Wa_2^T, q2 = agg_3 Wa_3^T + agg_4 Wa_4^T,
+    bf16 H1/H2."""
     W0, b0, W1, b1, W2, b2, g, b = w
     rd = lambda t: t.to(torch.bfloat16).float()
-    q = rd(agg @ rd(W0[:, 128:]).t())
-    h = torch.relu(q + v @ rd(W0[:, :128]).t() + b0)
+    pre = v @ rd(W0[:, :128]).t() + b0
+    for t in range(0, len(aggs), 2):
+        q = sum(aggs[j] @ rd(W0[:, 128 * (1 + j): 128 * (2 + j)]).t() for j in range(t, min(t + 2, len(aggs))))
+        pre = pre + rd(q)
+    h = torch.relu(pre)
     h = torch.relu(rd(h) @ rd(W1).t() + b1)
     return v + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
 
 
 @pytest.mark.parametrize("mode", ["stash", "recompute"])
-@pytest.mark.parametrize("n_nodes", [1, 63, 128, 129, 1000, 1600, 40000])
-def test_projected_node_update_vs_bf16_emulation(n_nodes, mode, monkeypatch):
-    """ops.node_update (aggregate projection + the fused edge kernels driven with identity indices) against torch arithmetic
-    with the same rounding points, on ragged tile counts; run twice for bit determinism; both backward modes."""
+@pytest.mark.parametrize("n_agg", [1, 2, 3, 4])
+@pytest.mark.parametrize("n_nodes", [1, 63, 129, 1600, 40000])
+def test_projected_node_update_vs_bf16_emulation(n_nodes, n_agg, mode, monkeypatch):
+    """ops.node_update (aggregate projections + the fused edge kernels driven with identity indices) against torch arithmetic
+    with the same rounding points, on ragged tile counts, for 1..4 aggregates ('sum' ... 'pna'); run twice for bit
+    determinism; both backward modes."""
     monkeypatch.setattr(ops, "backward_mode", mode)
-    torch.manual_seed(n_nodes)
-    w = _random_mlp_weights(2, 13)
+    torch.manual_seed(n_nodes + n_agg)
+    w = _random_mlp_weights(1 + n_agg, 13)
     v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
-    a0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    a0 = [torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16) for _ in range(n_agg)]
     gup = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
     runs = []
     for _ in range(2):
         params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
         params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
-        v, agg = v0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
-        out = ops.node_update(params, {}, v, agg)
+        v = v0.clone().requires_grad_(True)
+        aggs = [a.clone().requires_grad_(True) for a in a0]
+        out = ops.node_update(params, {}, v, aggs)
         out.backward(gup)
-        runs.append([out.detach(), v.grad, agg.grad] + [p.grad for p in params])
+        runs.append([out.detach(), v.grad] + [a.grad for a in aggs] + [p.grad for p in params])
     for a, b in zip(*runs):
         assert torch.equal(a, b)
     wr = [p.detach().clone().requires_grad_(True) for p in params]
-    vf, af = v0.float().requires_grad_(True), a0.float().requires_grad_(True)
+    vf = v0.float().requires_grad_(True)
+    af = [a.float().requires_grad_(True) for a in a0]
     ref = _bf16_emulated_projected_node(vf, af, wr)
     ref.backward(gup.float())
     assert rel_err(out.float(), ref) < 1e-2
-    assert rel_l2(v.grad.float(), vf.grad) < 1e-2 and rel_l2(agg.grad.float(), af.grad) < 1.5e-2
+    assert rel_l2(v.grad.float(), vf.grad) < 1e-2
+    for a, b in zip(aggs, af):
+        assert rel_l2(a.grad.float(), b.grad) < 1.5e-2
     for a, b in zip(params, wr):
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
