@@ -103,8 +103,8 @@ class _SegmentAggregate(torch.autograd.Function):
         grad = torch.empty(ctx.in_shape, dtype=ref.dtype, device=ref.device)
         with torch.cuda.device(ref.device):
             _cabi.check(lib.hgn_segment_reduce_bwd(
-                _cabi.dtype_code(ref.dtype), ctx.E, ctx.D, plan.ids32.data_ptr(), plan.rowptr.data_ptr(), plan.num_segments,
-                _cabi.ptr(g["sum"]), _cabi.ptr(g["mean"]), _cabi.ptr(g["max"]), _cabi.ptr(g["min"]),
+                _cabi.dtype_code(ref.dtype), ctx.E, ctx.D, plan.ids32.data_ptr(), plan.perm.data_ptr(), plan.rowptr.data_ptr(),
+                plan.num_segments, _cabi.ptr(g["sum"]), _cabi.ptr(g["mean"]), _cabi.ptr(g["max"]), _cabi.ptr(g["min"]),
                 _cabi.ptr(argmax), _cabi.ptr(argmin), grad.data_ptr(), 0, _cabi.stream_ptr()), "hgn_segment_reduce_bwd")
         _count()
         return grad, None, None

@@ -78,8 +78,10 @@ int hgn_segment_reduce(int dtype, const void* data, int64_t num_edges, int32_t D
 /* Backward of the above (autograd of scatter_add / scatter_mean / scatter_max / scatter_min):
  * grad_data[e,:] (+)= g_sum[r_e,:] + g_mean[r_e,:]/max(cnt_r,1) + [argmax[r_e,:]==e] g_max[r_e,:]
  *                    + [argmin[r_e,:]==e] g_min[r_e,:]        (NULL gradients are skipped). */
+/* perm (the plan's grouping of element ids by segment, may be NULL) lets the bf16 / D = 128 case run segment-wise: each
+ * segment's gradient rows are read once instead of once per element. */
 int hgn_segment_reduce_bwd(int dtype, int64_t num_edges, int32_t D,
-                           const int32_t* ids32, const int32_t* rowptr, int64_t num_segments,
+                           const int32_t* ids32, const int32_t* perm, const int32_t* rowptr, int64_t num_segments,
                            const void* g_sum, const void* g_mean, const void* g_max, const void* g_min,
                            const int32_t* argmax, const int32_t* argmin,
                            void* grad_data, int accumulate, void* stream);
