@@ -167,13 +167,30 @@ def run_ours(args):
     def step_resident():
         return step(v_dev.detach(), e_dev.detach())
 
-    def step_e2e():
-        v = v0_host.to(dev, non_blocking=True)
-        ed = e0_host.to(dev, non_blocking=True)
-        loss = step(v, ed)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return loss_host
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload():
+        """H2D copy of one step's fp32 inputs from pinned host memory on the copy stream (an input pipeline's prefetch)."""
+        with torch.cuda.stream(copy_stream):
+            v = v0_host.to(dev, non_blocking=True)
+            ed = e0_host.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return v, ed, ready
+
+    def run_e2e(steps):
+        """`steps` end-to-end steps: every step's inputs cross PCIe inside the region (step i+1's copy overlaps step i's
+        compute, the way a training loop prefetches its next batch) and every step's loss is read back to the host."""
+        nxt = upload()
+        for i in range(steps):
+            v, ed, ready = nxt
+            if i + 1 < steps:
+                nxt = upload()
+            torch.cuda.current_stream().wait_event(ready)
+            v.record_stream(torch.cuda.current_stream()); ed.record_stream(torch.cuda.current_stream())
+            loss = step(v, ed)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -197,13 +214,12 @@ def run_ours(args):
     value = e * LAYERS / (ms_per_step * 1e-3)
 
     # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss ---------------------------------
-    step_e2e()
+    run_e2e(3)                                  # warm-up: two input sets are alive at a time, let the allocator cache both
     torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 4))
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(1, min(args.steps, 3))
-    t0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
+    t0.record()                                 # on the compute stream, which waits for every copy it consumes
+    run_e2e(e2e_steps)
     t1.record()
     torch.cuda.synchronize()
     e2e_ms = t0.elapsed_time(t1) / e2e_steps
@@ -224,7 +240,8 @@ def run_ours(args):
                                "processor fwd+bwd", "nodes": n, "edges": e, "layers": LAYERS, "latent": LATENT,
                    "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none",
                    "backward": ops.backward_mode},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss D2H + stream sync every step",
                 "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks.summary(),

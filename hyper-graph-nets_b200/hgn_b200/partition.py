@@ -305,13 +305,32 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
     _cabi.profile(False)
     roofline = roofline_fn(kernels, args.steps, int(lg.edge_ids.numel()), int(lg.owned.numel()), peaks) if roofline_fn else None
 
-    def step_e2e():
-        loss = step(v_host.to(dev, non_blocking=True), e_host.to(dev, non_blocking=True))
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    copy_stream = torch.cuda.Stream(device=dev)
 
-    step_e2e()
-    e2e_ms = timed(step_e2e, max(1, min(args.steps, 3)))
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            v, ed = v_host.to(dev, non_blocking=True), e_host.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return v, ed, ready
+
+    e2e_steps = max(2, min(args.steps, 4))
+
+    def run_e2e(steps=e2e_steps):
+        """Every step's inputs cross PCIe inside the region (step i+1's copy overlaps step i) and every loss is read back."""
+        nxt = upload()
+        for i in range(steps):
+            v, ed, ready = nxt
+            if i + 1 < steps:
+                nxt = upload()
+            torch.cuda.current_stream().wait_event(ready)
+            v.record_stream(torch.cuda.current_stream()); ed.record_stream(torch.cuda.current_stream())
+            loss = step(v, ed)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    run_e2e(3)                                  # warm-up: two input sets are alive at a time, let the allocator cache both
+    e2e_ms = timed(run_e2e, 1) / e2e_steps
     halo_rows = torch.tensor([float(lg.n_ghost)], device=dev)
     dist.all_reduce(halo_rows, op=dist.ReduceOp.MAX)
     if rank == 0:
