@@ -115,3 +115,56 @@ def test_two_rank_halo_exchange_matches_single_process(tmp_path):
         assert torch.allclose(p["grad_e"], ed.grad[p["edge_ids"]], rtol=1e-4, atol=1e-5)
         for g, ref in zip(p["grad_w"], weights.values()):
             assert torch.allclose(g, ref.grad, rtol=1e-4, atol=1e-4)                          # identical on both ranks after all-reduce
+
+
+# ---- trajectory data parallelism (cfg 4: replicas + gradient all-reduce) -------------------------------------
+def _dp_batch(seed):
+    w, h = 7, 6
+    s, r = synthetic.grid_edges_two_way(w, h)
+    v = synthetic.seeded_tensor(f"dp_v{seed}", (w * h, 128), seed)
+    e = synthetic.seeded_tensor(f"dp_e{seed}", (s.numel(), 128), seed)
+    return s, r, v, e
+
+
+def _dp_loss(weights, batch):
+    s, r, v, e = batch
+    out = orc.processor(weights, "sum", "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", e, s, r)]))
+    return out.node_features[0].square().mean() + out.edge_sets[0].features.square().mean()
+
+
+def _dp_weights():
+    return {k: t.clone().requires_grad_(True) for k, t in
+            synthetic.seeded_state_dict(synthetic.processor_shapes(2, ["mesh_edges"], "sum"), 5).items()}
+
+
+def _dp_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        weights = _dp_weights()
+        _dp_loss(weights, _dp_batch(10 + rank)).backward()          # rank i takes trajectory batch i
+
+        class _Holder(torch.nn.Module):
+            def __init__(self, ws):
+                super().__init__()
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(t.detach()) for t in ws.values()])
+                for p, t in zip(self.ps, ws.values()):
+                    p.grad = t.grad
+        holder = _Holder(weights)
+        partition.allreduce_gradients(holder)
+        torch.save([p.grad for p in holder.ps], os.path.join(tmpdir, f"dp_rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_gradients_match_summed_batches(tmp_path):
+    """Replicas on different trajectory batches + `allreduce_gradients` == one process summing the batches' gradients."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    weights = _dp_weights()
+    sum(_dp_loss(weights, _dp_batch(10 + k)) for k in range(world)).backward()
+    per_rank = [torch.load(os.path.join(tmp_path, f"dp_rank{k}.pt")) for k in range(world)]
+    for g0, g1, ref in zip(per_rank[0], per_rank[1], weights.values()):
+        assert torch.equal(g0, g1)                                   # replicas stay identical
+        assert torch.allclose(g0, ref.grad, rtol=1e-5, atol=1e-6)
