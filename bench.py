@@ -216,7 +216,7 @@ def run_ours(args):
     # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss ---------------------------------
     run_e2e(3)                                  # warm-up: two input sets are alive at a time, let the allocator cache both
     torch.cuda.synchronize()
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = max(2, min(args.steps, 8))
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()                                 # on the compute stream, which waits for every copy it consumes
     run_e2e(e2e_steps)

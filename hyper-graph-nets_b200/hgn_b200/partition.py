@@ -314,7 +314,7 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
             ready.record(copy_stream)
         return v, ed, ready
 
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = max(2, min(args.steps, 8))
 
     def run_e2e(steps=e2e_steps):
         """Every step's inputs cross PCIe inside the region (step i+1's copy overlaps step i) and every loss is read back."""
