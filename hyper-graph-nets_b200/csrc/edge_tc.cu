@@ -721,10 +721,11 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 
 // fixed-order reduction of the per-CTA partials of edge_bwd_tc_kernel
 __global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, const float* __restrict__ epi_colpart,
-                                       const float* __restrict__ prod_colpart, int parts, int w0_chunks, int w0_chunk0, float* __restrict__ gW0, float* __restrict__ gW1,
+                                       const float* __restrict__ prod_colpart, int parts, int w0_chunks, int w0_chunk0, int skip_we, float* __restrict__ gW0, float* __restrict__ gW1,
                                        float* __restrict__ gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * kD * kD) {
+    if (skip_we && i < kD * kD) return;          // dWe comes from the streaming weight-gradient kernel
     float s = 0.f;
     for (int p = 0; p < parts; ++p) s += w_partial[int64_t(p) * 3 * kD * kD + i];
     const int z = i / (kD * kD), o = (i / kD) % kD, c = i % kD;
@@ -756,8 +757,8 @@ __global__ void reduce_w0_block_kernel(const float* __restrict__ partial, int pa
 // ---- host side -----------------------------------------------------------------------------------------------------------
 void launch_edge_bwd_reduce(const float* w_partial, const float* epi_colpart, const float* prod_colpart, int parts, int w0_chunks, int w0_chunk0,
                             float* gW0, float* gW1, float* gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta, cudaStream_t st) {
-  edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi_colpart, prod_colpart, parts, w0_chunks, w0_chunk0, gW0,
-                                                                            gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
+  edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi_colpart, prod_colpart, parts, w0_chunks, w0_chunk0, 0,
+                                                                            gW0, gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
 }
 
 int tc_pair_wgrad(int64_t rows, const void* Ga, const void* Za, const void* Gb, const void* Zb, float* partial, int parts,
@@ -825,6 +826,10 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // 
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
                        const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name,
                        cudaStream_t st);                                                                                  // edge_fwd_tc.cu
+int edge_bwd2_launch(int64_t rows, int64_t tiles, int grid, const void* packed, const void* dense, const void* proj_s, const void* proj_r,
+                     const int32_t* senders, const int32_t* receivers, int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg,
+                     void* grad_dense, void* grad_pre0, float* w_partial, float* epi_colpart, float* prod_colpart, const char* name,
+                     cudaStream_t st);                                                                                    // edge_bwd2_tc.cu
 int stash_backward_launch(int64_t rows, const void* dense, const void* h1, const void* h2, const int32_t* receivers, const void* packed,
                           int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg, void* grad_dense, void* grad_pre0,
                           float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
@@ -848,7 +853,7 @@ int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj
   return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc_legacy", st);
 }
 
-struct EdgeBwdLayout { size_t w_partial, epi, prod, total; int grid; };
+struct EdgeBwdLayout { size_t w_partial, epi, prod, pair, total; int grid, pair_parts; };
 static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
   EdgeBwdLayout L{};
   const int64_t tiles = ceil_div(rows > 0 ? rows : 1, kTile);
@@ -858,6 +863,8 @@ static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
   L.w_partial = take(size_t(L.grid) * 3 * kD * kD * 4);
   L.epi = take(size_t(L.grid) * 4 * 2 * kD * 4);
   L.prod = take(size_t(L.grid) * 3 * kD * 4);
+  L.pair_parts = tc_pair_wgrad_parts(rows);
+  L.pair = take(size_t(L.pair_parts) * 2 * kD * kD * 4);      // dWe = G0^T e partials of the streaming weight-gradient kernel (two-tile backward)
   L.total = off;
   return L;
 }
@@ -873,6 +880,27 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
   const EdgeBwdLayout L = edge_bwd_layout(rows);
   if (int rc = configure_edge_kernels()) return rc;
   char* ws = static_cast<char*>(workspace);
+  // HGN_EDGE_BWD_INTERLEAVED=1: the experimental two-tile interleaved kernel (edge_bwd2_tc.cu; parity-tested, currently 4.3 ms vs
+  // 3.45 ms per cfg5 layer for the one-tile kernel below: see DESIGN.md s3.2); dWe = G0^T dense then comes from the streaming
+  // weight-gradient kernel.  Read per call so that tests can switch it.
+  const char* inter = getenv("HGN_EDGE_BWD_INTERLEAVED");
+  if (inter != nullptr && inter[0] == '1') {
+    float* w_partial = reinterpret_cast<float*>(ws + L.w_partial);
+    float* epi = reinterpret_cast<float*>(ws + L.epi);
+    float* prod = reinterpret_cast<float*>(ws + L.prod);
+    float* pair = reinterpret_cast<float*>(ws + L.pair);
+    if (int rc = edge_bwd2_launch(rows, ceil_div(rows, kTile), L.grid, packed, dense, proj_s, proj_r, senders, receivers, w0_chunks, w0_chunk0,
+                                  grad_out, grad_agg, grad_dense, grad_pre0, w_partial, epi, prod, name, st)) return rc;
+    if (int rc = tc_pair_wgrad(rows, grad_pre0, dense, nullptr, nullptr, pair, L.pair_parts, st)) return rc;
+    {
+      HGN_TIMED("reduce_weight_partials", st);
+      edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi, prod, L.grid, w0_chunks, w0_chunk0, 1, gW0, gW1, gW2,
+                                                                                gb0, gb1, gb2, ggamma, gbeta);
+      reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(pair, L.pair_parts, 2, 1, gW0, w0_chunks * kD, w0_chunk0 * kD);
+    }
+    HGN_LAUNCH_OK("edge_bwd_reduce");
+    return HGN_OK;
+  }
   EdgeBwdArgs a{};
   a.edge = static_cast<const __nv_bfloat16*>(dense);
   a.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
@@ -917,7 +945,7 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
   }
   {
     HGN_TIMED("reduce_weight_partials", st);
-    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, a.w0_chunks, a.w0_chunk0,
+    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, a.w0_chunks, a.w0_chunk0, 0,
                                                                               gW0, gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
   }
   HGN_LAUNCH_OK("edge_bwd_reduce");

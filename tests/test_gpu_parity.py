@@ -370,6 +370,32 @@ def test_projected_node_update_vs_bf16_emulation(n_nodes, n_agg, mode, monkeypat
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
 
+def test_interleaved_backward_kernel_matches_default(monkeypatch):
+    """The experimental two-tile interleaved backward kernel (HGN_EDGE_BWD_INTERLEAVED=1, csrc/edge_bwd2_tc.cu) against the default
+    one-tile kernel: same arithmetic and rounding points, so data gradients agree to bf16 rounding of identical values and
+    weight gradients to fp32 summation order."""
+    monkeypatch.setattr(ops, "backward_mode", "recompute")
+    torch.manual_seed(5)
+    w = _random_mlp_weights(3, 11)
+    n_nodes, rows = 3000, 70001
+    s = torch.randint(0, n_nodes, (rows,), device="cuda")
+    r = torch.randint(0, n_nodes, (rows,), device="cuda")
+    sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
+    v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    e0 = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
+    runs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("HGN_EDGE_BWD_INTERLEAVED", flag)
+        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+        v, e = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+        out, agg = ops.edge_update(params, {}, v, e, sp, rp, True)
+        (out.float().sum() + (agg.float() ** 2).sum()).backward()
+        runs[flag] = [v.grad, e.grad] + [p.grad for p in params]
+    for a, b in zip(runs["0"], runs["1"]):
+        assert rel_l2(a.float(), b.float()) < 2e-3
+
+
 @pytest.mark.parametrize("mode", ["stash", "recompute"])
 def test_projected_edge_update_is_deterministic(mode, monkeypatch):
     monkeypatch.setattr(ops, "backward_mode", mode)
