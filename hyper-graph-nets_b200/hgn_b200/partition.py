@@ -365,8 +365,11 @@ class PartitionedProcessor(torch.nn.Module):
     every block; the block itself is unchanged (it sees ``[owned | ghosts]`` as ``[mesh | hyper]`` rows).
 
     With an ``OverlapPlan`` (edges listed interior-first), bf16 latents, plain ``GraphNet`` blocks, the 'sum' aggregator and one
-    edge set, every block instead runs ``_PartitionedEdgeUpdate`` -- the halo exchange travels behind the interior edge tiles --
-    followed by the projected node update on the owned rows.  ``HGN_HALO_OVERLAP=0`` forces the generic path."""
+    edge set, ``HGN_HALO_OVERLAP=1`` makes every block run ``_PartitionedEdgeUpdate`` -- the halo exchange travels behind the
+    interior edge tiles -- followed by the projected node update on the owned rows.  Opt-in: it is validated against the generic
+    path (scripts/check_overlap.py, 2 GPUs) but measured SLOWER at N = 8 (47 vs 23 ms per step): the persistent edge kernels
+    occupy every SM, so the NCCL send/recv kernels get no SM until a compute CTA retires and each side ends up waiting for the
+    other; it needs compute grids that leave SMs to the communication kernels."""
 
     def __init__(self, processor: torch.nn.Module, plan: HaloPlan, overlap: Optional[OverlapPlan] = None):
         super().__init__()
@@ -378,7 +381,7 @@ class PartitionedProcessor(torch.nn.Module):
         import os
         from .migration.graphnet import GraphNet
         blocks = self.processor.graphnet_blocks
-        return (self.overlap is not None and os.environ.get("HGN_HALO_OVERLAP", "1") != "0" and owned.is_cuda
+        return (self.overlap is not None and os.environ.get("HGN_HALO_OVERLAP", "0") == "1" and owned.is_cuda
                 and len(edge_sets) == 1 and all(type(b) is GraphNet and b.message_passing_aggregator == "sum"
                                                 and list(b.edge_models.keys()) == [edge_sets[0].name] for b in blocks))
 
@@ -486,10 +489,13 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
         step(v_dev.detach(), e_dev.detach())
     from . import _cabi
     launches0 = ops.launch_count
-    _cabi.profile(True)
     with clock_sampler_cls(dev.index) as clocks:
         ms_per_step = timed(lambda: step(v_dev.detach(), e_dev.detach()), args.steps)
     launches = ops.launch_count - launches0
+    # per-kernel times from a second pass of the same steps: at several ranks the kernels are short and the two CUDA events the
+    # library records around every launch would make the timed region host-bound
+    _cabi.profile(True)
+    timed(lambda: step(v_dev.detach(), e_dev.detach()), args.steps)
     kernels = _cabi.profile_report()
     _cabi.profile(False)
     roofline = roofline_fn(kernels, args.steps, int(lg.edge_ids.numel()), int(lg.owned.numel()), peaks) if roofline_fn else None
@@ -540,5 +546,6 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
             "gpu_launches": launches, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": None,
             "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
+            "kernel_times": "second pass of the same steps with the library's per-launch CUDA events enabled",
         }))
     dist.destroy_process_group()
