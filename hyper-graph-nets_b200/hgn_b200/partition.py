@@ -367,7 +367,7 @@ class PartitionedProcessor(torch.nn.Module):
     With an ``OverlapPlan`` (edges listed interior-first), bf16 latents, plain ``GraphNet`` blocks, the 'sum' aggregator and one
     edge set, ``HGN_HALO_OVERLAP=1`` makes every block run ``_PartitionedEdgeUpdate`` -- the halo exchange travels behind the
     interior edge tiles -- followed by the projected node update on the owned rows.  Opt-in: it is validated against the generic
-    path (scripts/check_overlap.py, 2 GPUs) but measured SLOWER at N = 8 (47 vs 23 ms per step): the persistent edge kernels
+    path (scripts/check_overlap.py, 2 GPUs) but measured SLOWER at N = 8 (28.4 vs 21.2 ms per step): the persistent edge kernels
     occupy every SM, so the NCCL send/recv kernels get no SM until a compute CTA retires and each side ends up waiting for the
     other; it needs compute grids that leave SMs to the communication kernels."""
 
