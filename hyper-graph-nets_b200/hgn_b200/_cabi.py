@@ -14,6 +14,7 @@ HGN_F32 = 0
 HGN_BF16 = 1
 AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN = 1, 2, 4, 8
 HGN_MAX_CHUNKS = 24
+ABI_VERSION = 2            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhgn_b200.so")
 
@@ -85,8 +86,8 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)   # AttributeError here = header and library out of sync
             fn.restype = res
             fn.argtypes = args
-        if lib.hgn_abi_version() != 1:
-            raise HgnError("libhgn_b200.so ABI version mismatch")
+        if lib.hgn_abi_version() != ABI_VERSION:
+            raise HgnError(f"libhgn_b200.so ABI version {lib.hgn_abi_version()} != {ABI_VERSION} expected by these bindings: rebuild")
         _lib = lib
     return _lib
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HGN_B200_ABI_VERSION 1
+#define HGN_B200_ABI_VERSION 2
 
 typedef enum {
   HGN_OK = 0,

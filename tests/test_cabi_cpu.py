@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/hgn_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == declared, "ctypes signatures out of sync with the header"
-    assert lib.hgn_abi_version() == 1
+    assert lib.hgn_abi_version() == 2
 
 
 def test_size_queries_need_no_gpu():
@@ -37,6 +37,9 @@ def test_size_queries_need_no_gpu():
     assert lib.hgn_mlp_packed_bytes(_cabi.HGN_F32, 0) == 0
     assert lib.hgn_mlp_backward_workspace_bytes(_cabi.HGN_F32, 1000, 3) > 0
     assert lib.hgn_csr_workspace_bytes(1000, 100) > 3 * 4000
+    assert lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_BF16, 1000) > 3 * 128 * 128 * 4
+    assert lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, 1000) > 1000 * 128 * 2
+    assert lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_F32, 1000) == 0      # bf16-only entry points say so
 
 
 @pytest.mark.parametrize("name", MODEL_CASES)
