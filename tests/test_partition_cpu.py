@@ -42,6 +42,27 @@ def test_partition_bookkeeping_bit_exact(world):
             assert torch.equal(sent_global, lgs[q].ghosts[glo:glo + lgs[q].ghost_splits[p]])   # same rows, same order
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_interior_first_edge_order(world):
+    """interior_first lists the edges with an owned sender before the cut edges, each group in original order, and changes
+    nothing else (same edge set, same ghosts, same exchange lists)."""
+    w, h = 13, 11
+    s, r = synthetic.grid_edges_two_way(w, h)
+    part = partition.block_partition(w * h, world)
+    for p in range(world):
+        base = partition.build_local_graph(s, r, part, p, world)
+        lg = partition.build_local_graph(s, r, part, p, world, interior_first=True)
+        k = lg.n_interior
+        assert base.n_interior is None and 0 < k < lg.edge_ids.numel()
+        assert (lg.senders[:k] < lg.n_own).all() and (lg.senders[k:] >= lg.n_own).all()
+        assert torch.equal(lg.edge_ids[:k], torch.sort(lg.edge_ids[:k]).values)
+        assert torch.equal(lg.edge_ids[k:], torch.sort(lg.edge_ids[k:]).values)
+        assert torch.equal(torch.sort(lg.edge_ids).values, base.edge_ids)
+        assert torch.equal(lg.ghosts, base.ghosts) and torch.equal(lg.send_index, base.send_index)
+        glob = torch.cat([lg.owned, lg.ghosts])
+        assert torch.equal(glob[lg.senders], s[lg.edge_ids]) and torch.equal(glob[lg.receivers], r[lg.edge_ids])
+
+
 def test_coordinate_bisection_balanced():
     pos = synthetic.cloth_frame(16, 12, 0)["mesh_pos"]
     part = partition.coordinate_bisection(pos, 4)
