@@ -252,6 +252,8 @@ def run_ours(args):
         "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
         "cpu_baseline": cpu,
     }
+    if args.aggregator == "sum" and not os.environ.get("HGN_BENCH_NO_ROLLOUT"):
+        line["rollout"] = rollout_bench(dev)         # the metric's second half, BASELINE.json configs[1]
     print(json.dumps(line))
 
 
@@ -292,6 +294,103 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
     return {"kernel": top["name"], "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "mean_launch_ms": mean_ms,
             "share_of_step": top["ms"] / sum(k["ms"] for k in kernels), "peak_source": peaks["source"]}
+
+
+# ------------------------------------------------------------------------------------------------------
+# second half of the metric: rollout steps/sec (BASELINE.json configs[1]: flag_simple-shaped cloth, 15 MP layers, 400 steps)
+# ------------------------------------------------------------------------------------------------------
+ROLLOUT_W, ROLLOUT_H, ROLLOUT_STEPS = 40, 40, 400      # 1 600 nodes / 9 282 directed edges ~ flag_simple (1 579 / 9 212)
+
+
+def _cloth_features(world, prev, mesh_pos, pinned_type, senders, receivers):
+    """FlagModel.build_graph (src/model/flag.py:65-128) on device tensors: velocity + node-type one-hot, relative world / mesh
+    positions and their norms."""
+    node_features = torch.cat((world - prev, pinned_type), dim=-1)
+    rel_world = world[senders] - world[receivers]
+    rel_mesh = mesh_pos[senders] - mesh_pos[receivers]
+    edge_features = torch.cat((rel_world, rel_world.pow(2).sum(-1, keepdim=True).sqrt(),
+                               rel_mesh, rel_mesh.pow(2).sum(-1, keepdim=True).sqrt()), dim=-1)
+    return node_features, edge_features
+
+
+def rollout_bench(dev):
+    """Closed-loop rollout (flag.py:194-246: predict, second-order integrate, pin the handle nodes, rebuild the graph) of the whole
+    encode-process-decode model in bf16 processor mode, eager and as one CUDA graph per step.  Returns the JSON sub-object."""
+    from hgn_b200 import synthetic
+    from hgn_b200 import util as hutil
+    from hgn_b200.migration.meshgraphnet import MeshGraphNet
+    frame = synthetic.cloth_frame(ROLLOUT_W, ROLLOUT_H, seed=1)
+    edges = hutil.triangles_to_edges(frame["cells"].long())
+    senders, receivers = (t.to(dev) for t in edges["two_way_connectivity"])
+    mesh_pos = frame["mesh_pos"].to(dev)
+    node_type = frame["node_type"].to(dev)
+    pinned = torch.ne(node_type[:, 0], 0).unsqueeze(-1)
+    pinned_type = torch.nn.functional.one_hot(pinned[:, 0].long(), 2).float()
+    torch.manual_seed(0)
+    model = MeshGraphNet(3, LATENT, 2, "sum", LAYERS, "none", ["mesh_edges"]).to(dev)
+    model.processor.precision = "bf16"
+    world = frame["world_pos"].to(dev).clone()
+    prev = frame["prev|world_pos"].to(dev).clone()
+    world0, prev0 = world.clone(), prev.clone()
+
+    def one_step():
+        nf, ef = _cloth_features(world, prev, mesh_pos, pinned_type, senders, receivers)
+        acc = model(hutil.MultiGraph([nf], [hutil.EdgeSet("mesh_edges", ef, senders, receivers)]))
+        nxt = torch.where(pinned, world, 2 * world - prev + 0.01 * acc)
+        prev.copy_(world)
+        world.copy_(nxt)
+
+    def timed(fn, steps):
+        world.copy_(world0); prev.copy_(prev0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return steps / (a.elapsed_time(b) * 1e-3)
+
+    out = {"config": f"{ROLLOUT_W}x{ROLLOUT_H} flag-style cloth ({world.shape[0]} nodes, {senders.numel()} directed edges), encoder + {LAYERS} GraphNet "
+                     f"layers (sum, bf16 processor) + decoder, {ROLLOUT_STEPS} closed-loop steps, graph features rebuilt on the device every step",
+           "unit": "rollout steps/s"}
+    with torch.no_grad():
+        for _ in range(5):
+            one_step()                                   # lazy linears, plans, packed weights
+        out["eager"] = timed(one_step, ROLLOUT_STEPS)
+        eager_final = world.clone()
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    one_step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one_step()
+            out["cuda_graph"] = timed(graph.replay, ROLLOUT_STEPS)
+            out["cuda_graph_bitwise_equal_to_eager"] = bool(torch.equal(world, eager_final))
+        except Exception as exc:                         # capture is an optimisation of the host side only
+            out["cuda_graph"] = None
+            out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
+    # CPU oracle on the same model and mesh, bounded to a few steps
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgn_oracle as orc
+    weights = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    cw, cp = world0.cpu(), prev0.cpu()
+    cs, cr, cm, cpin, cpt = senders.cpu(), receivers.cpu(), mesh_pos.cpu(), pinned.cpu(), pinned_type.cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    steps_cpu = 5
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(steps_cpu):
+            nf, ef = _cloth_features(cw, cp, cm, cpt, cs, cr)
+            acc = orc.mesh_graph_net(weights, "sum", "none", orc.MultiGraph([nf], [orc.EdgeSet("mesh_edges", ef, cs, cr)]))
+            cw, cp = torch.where(cpin, cw, 2 * cw - cp + 0.01 * acc), cw
+        out["cpu_oracle"] = steps_cpu / (time.perf_counter() - t0)
+    out["cpu_cores"] = torch.get_num_threads()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
