@@ -597,18 +597,19 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       // ---- E3: dH2' = (dY W2) * [H2 > 0] -> B ---------------------------------------------------------------------
       {
         wait_acc(103); if (tid == 0) stamp(a, t, 16);
-        uint32_t hw[32], o[32];
-        load_row(B, hw);                                        // H2, about to be replaced by its own gradient
 #pragma unroll
-        for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
+        for (int cg = 0; cg < 2; ++cg) {                        // per 32-column group: mask words (H2, about to be replaced by its
+          uint32_t v[32], hw[16], o[16];                        // own gradient) are fetched under the TMEM load
           tmem_ld32(acc + cg * 32, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ld_shared128(B + row_off + sw128_chunk(r, 4 * cg + k), hw + 4 * k);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            o[cg * 16 + j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[cg * 16 + j]);
+            o[j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) st_shared128(B + row_off + sw128_chunk(r, 4 * cg + k), o + 4 * k);
         }
-        store_row(B, o);
         if (tid == 0) stamp(a, t, 17);
         done(1);
       }
@@ -626,19 +627,20 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
       {
         wait_cs(0, t);                                          // the producers' dY column sum has left buffer C
         wait_acc(104); if (tid == 0) stamp(a, t, 18);
-        uint32_t hw[32], o[32];
-        load_row(A, hw);                                        // H1: the last reader of buffer A in this tile
-        __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbAfree]);
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
-          uint32_t v[32];
+          uint32_t v[32], hw[16], o[16];
           tmem_ld32(acc + cg * 32, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ld_shared128(A + row_off + sw128_chunk(r, 4 * cg + k), hw + 4 * k);   // H1 mask words
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            o[cg * 16 + j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[cg * 16 + j]);
+            o[j] = relu_bwd_bf16x2(pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hw[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) st_shared128(C + row_off + sw128_chunk(r, 4 * cg + k), o + 4 * k);
         }
-        store_row(C, o);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbAfree]);   // this warp has read its H1 rows: the last reader of buffer A in this tile
         if (tid == 0) stamp(a, t, 19);
         if (lane == 0) stamp(a, t, 40 + warp);
         done(2);
