@@ -1,0 +1,44 @@
+"""bench.py's CPU legs (the `cpu_baseline` object and the `--impl reference` arm) on a reduced sample: the JSON contract of
+the reference arm must hold without a GPU."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+
+
+def test_cpu_baseline_and_reference_arm_contract(monkeypatch, capsys):
+    monkeypatch.setattr(bench, "CPU_SAMPLE_W", 60)
+    monkeypatch.setattr(bench, "CPU_SAMPLE_H", 20)
+    cpu = bench.cpu_baseline(steps=1)
+    assert cpu["kind"] == "port" and cpu["unit"] == bench.UNIT and cpu["value"] > 0 and cpu["cores"] >= 1 and "sample" in cpu
+    monkeypatch.delenv("RANK", raising=False)
+    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=1, impl="reference", aggregator="sum"))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 print nothing
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=2, impl="reference", aggregator="sum"))
+    assert capsys.readouterr().out.strip() == ""
+
+
+def test_roofline_accounting_of_the_projected_kernels():
+    peaks = {"hbm_gbs": 6448.1, "bf16_tflops": 1625.3, "bf16_tflops_sustained": 1378.8, "source": "test"}
+    e, n = 5992002, 1000000
+    kernels = [{"name": "edge_bwd_tc", "launches": 15, "ms": 15 * 3.5}, {"name": "edge_fwd_tc", "launches": 15, "ms": 15 * 1.1}]
+    r = bench.dominant_kernel_roofline(kernels, 1, e, n, peaks)
+    assert r["kernel"] == "edge_bwd_tc" and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["achieved"] - e * 20 * 128 * 128 / 3.5e-3 / 1e12) < 1e-6           # backward = 2 x 10 D^2 per edge
+    assert abs(r["frac"] - r["achieved"] / 1378.8) < 1e-12 and r["executed_tflops"] < r["achieved"]
+    assert r["traffic"] == 4.699e9 + 3.050e9                                         # ncu capture, cfg5 launch size only
+    assert bench.dominant_kernel_roofline(kernels, 1, 1000, 100, peaks)["traffic"] is None
+    seg = bench.dominant_kernel_roofline([{"name": "segment_reduce", "launches": 3, "ms": 0.93}], 1, e, n, peaks)
+    assert seg["bound"] == "hbm" and abs(seg["achieved"] - ((e + n) * 256 + e * 4) / 0.31e-3 / 1e9) < 1e-6
