@@ -238,7 +238,7 @@ edge_bwd_stash_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restr
     uint32_t acc_phase = 0;
     float cbeta[2] = {0.f, 0.f}, cgamma[2] = {0.f, 0.f};
     auto wait_acc = [&](int tag) {
-      mbar_spin(&bars[kSbAcc], acc_phase++ & 1, tag);
+      mbar_wait(&bars[kSbAcc], acc_phase++ & 1, tag);
       fence_after_sync();
     };
     auto wait_cs = [&](int k, int64_t tt) { mbar_wait(&bars[kSbCs + k], uint32_t(tt) & 1, 70 + k); };

@@ -393,7 +393,8 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
     uint32_t acc_phase = 0;
     float cbeta[2] = {0.f, 0.f}, cgamma[2] = {0.f, 0.f};
     auto wait_acc = [&](int tag) {
-      mbar_spin(&bars[kEbAcc], acc_phase++ & 1, tag);
+      mbar_wait(&bars[kEbAcc], acc_phase++ & 1, tag);         // try_wait (suspends): measured 2 % faster than busy polling here -- eight
+                                                               // polling warps take issue slots from the column-sum warps and the MMA thread
       fence_after_sync();
     };
     // k-th column-sum hand-over of (local) tile tt: the producers have finished reading that tile from its buffer
