@@ -35,6 +35,15 @@ import torch  # noqa: E402
 
 GRID_W, GRID_H = 1000, 1000
 LAYERS = 15
+# --workload: the headline (cfg5) plus the small-mesh training shapes of BASELINE.json configs[1] and [3] (SURVEY.md s8 cfg 2 / cfg 4:
+# a batch of B disjoint trajectories' meshes per step, src/algorithms/MeshSimulator.py:158-234).  Only cfg5 is the bench line the
+# driver reads; the others are reported under profiles/.
+#            name: (grid w, grid h, batch, layers, aggregator, CPU sample (w, h, batch, layers), description)
+WORKLOADS = {
+    "cfg5": (1000, 1000, 1, 15, "sum", (1000, 125, 1, 1), "cfg5: 1M-node / 5 992 002-edge triangulated mesh"),
+    "cfg2": (40, 40, 21, 15, "pna", (40, 40, 21, 15), "cfg2: flag_simple-shaped cloth (40x40 grid, 1 600 nodes / 9 282 edges) x batch 21"),
+    "cfg4": (48, 40, 21, 5, "pna", (48, 40, 21, 5), "cfg4: cylinder_flow-shaped 2-D mesh (48x40 grid, 1 920 nodes / 11 158 edges) x batch 21, one rank's share"),
+}
 LATENT = 128
 METRIC = "edge-updates/sec per MP layer (fwd+bwd)"
 UNIT = "edge-updates/s"
@@ -104,11 +113,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------------
-def build_inputs(width, height, layers, seed=0, aggregator="sum"):
-    """Host-side (pinned) latents, int64 edge lists and the seeded processor weights."""
+def build_inputs(width, height, layers, seed=0, aggregator="sum", batch=1):
+    """Host-side (pinned) latents, int64 edge lists and the seeded processor weights.  `batch` > 1: that many disjoint copies of the
+    mesh in one index space, graph i's nodes offset by i * N (MeshSimulator._get_batched, src/algorithms/MeshSimulator.py:196-217)."""
     from hgn_b200 import synthetic
     senders, receivers = synthetic.grid_edges_two_way(width, height)
-    n, e = width * height, senders.numel()
+    if batch > 1:
+        offs = (torch.arange(batch, dtype=senders.dtype) * (width * height)).repeat_interleave(senders.numel())
+        senders, receivers = senders.repeat(batch) + offs, receivers.repeat(batch) + offs
+    n, e = width * height * batch, senders.numel()
     gen = torch.Generator().manual_seed(seed)
     v0 = torch.randn(n, LATENT, generator=gen)
     e0 = torch.randn(e, LATENT, generator=gen)
@@ -140,12 +153,16 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         from hgn_b200 import partition
+        args.aggregator = args.aggregator or "sum"
         return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler,
                                            dominant_kernel_roofline)
 
-    data = build_inputs(GRID_W, GRID_H, LAYERS, aggregator=args.aggregator)
+    gw, gh, batch, layers, default_agg, cpu_sample, wl_text = WORKLOADS[args.workload]
+    args.aggregator = args.aggregator or default_agg
+    data = build_inputs(gw, gh, layers, aggregator=args.aggregator, batch=batch)
     n, e = data["n"], data["e"]
-    proc = make_processor(data["weights"], LAYERS, "bf16", dev, args.aggregator)
+    f_node = 2 * ((1 + (4 if args.aggregator == "pna" else 1)) + 2) * LATENT * LATENT
+    proc = make_processor(data["weights"], layers, "bf16", dev, args.aggregator)
     params = [p for p in proc.parameters()]
     senders, receivers = data["senders"].to(dev), data["receivers"].to(dev)
     v0_host, e0_host = data["v0"].pin_memory(), data["e0"].pin_memory()
@@ -211,7 +228,7 @@ def run_ours(args):
     launches = ops.launch_count - launches0
     kernels = _cabi.profile_report()
     _cabi.profile(False)
-    value = e * LAYERS / (ms_per_step * 1e-3)
+    value = e * layers / (ms_per_step * 1e-3)
 
     # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss ---------------------------------
     run_e2e(3)                                  # warm-up: two input sets are alive at a time, let the allocator cache both
@@ -223,37 +240,42 @@ def run_ours(args):
     t1.record()
     torch.cuda.synchronize()
     e2e_ms = t0.elapsed_time(t1) / e2e_steps
-    e2e_value = e * LAYERS / (e2e_ms * 1e-3)
+    e2e_value = e * layers / (e2e_ms * 1e-3)
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------
     peaks = load_peaks()
     roofline = dominant_kernel_roofline(kernels, args.steps, e, n, peaks)
 
     # ---- CPU baseline: oracle port on a bounded sub-mesh ------------------------------------------------
-    cpu = cpu_baseline(steps=1)
+    cpu = cpu_baseline(steps=1, sample=cpu_sample, aggregator=args.aggregator)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
-        "config": {"workload": f"cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, {args.aggregator} aggregator, "
-                               "processor fwd+bwd", "nodes": n, "edges": e, "layers": LAYERS, "latent": LATENT,
-                   "l2_policy": "inputs larger than L2 (1.8 GB of bf16 latents per layer)", "partitioning": "none",
-                   "backward": ops.backward_mode},
+        "dtype": "bf16", "data": f"synthetic (seeded {gw}x{gh} triangulated grid" + (f" x {batch}" if batch > 1 else "") + ", seeded weights)",
+        "config": {"workload": f"{wl_text}, {layers} GraphNet layers, {args.aggregator} aggregator, "
+                               "processor fwd+bwd", "nodes": n, "edges": e, "layers": layers, "latent": LATENT,
+                   "l2_policy": ("inputs larger than L2 (1.8 GB of bf16 latents per layer)" if args.workload == "cfg5" else
+                                 "small mesh: the whole step's working set is L2-resident by construction (launch-bound shape)"),
+                   "partitioning": "none", "backward": ops.backward_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss D2H + stream sync every step",
                 "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
-        "layer_roofline": {"tensor_ms_per_layer": 3 * (e * F_EDGE + n * F_NODE_SUM) / (load_peaks()["bf16_tflops_sustained"] * 1e12) * 1e3,
-                           "measured_ms_per_layer": ms_per_step / LAYERS,
-                           "frac": 3 * (e * F_EDGE + n * F_NODE_SUM) / (load_peaks()["bf16_tflops_sustained"] * 1e12) * 1e3 / (ms_per_step / LAYERS)},
+        "layer_roofline": {"tensor_ms_per_layer": 3 * (e * F_EDGE + n * f_node) / (load_peaks()["bf16_tflops_sustained"] * 1e12) * 1e3,
+                           "measured_ms_per_layer": ms_per_step / layers,
+                           "frac": 3 * (e * F_EDGE + n * f_node) / (load_peaks()["bf16_tflops_sustained"] * 1e12) * 1e3 / (ms_per_step / layers)},
         "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
         "cpu_baseline": cpu,
     }
-    if args.aggregator == "sum" and not os.environ.get("HGN_BENCH_NO_ROLLOUT"):
+    if args.workload == "cfg5" and args.aggregator == "sum" and not os.environ.get("HGN_BENCH_NO_ROLLOUT"):
         line["rollout"] = rollout_bench(dev)         # the metric's second half, BASELINE.json configs[1]
+    if not os.environ.get("HGN_BENCH_NO_TORCH_REFERENCE"):
+        del proc, params, v_dev, e_dev
+        torch.cuda.empty_cache()
+        line["torch_cuda_reference"] = torch_cuda_reference(dev, data, args.aggregator, layers if args.workload != "cfg5" else 1)
     print(json.dumps(line))
 
 
@@ -399,7 +421,7 @@ def rollout_bench(dev):
 CPU_SAMPLE_W, CPU_SAMPLE_H, CPU_SAMPLE_LAYERS = 1000, 125, 1
 
 
-def cpu_pass(state):
+def cpu_pass(state, aggregator="sum"):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hgn_oracle as orc
     w, v0, e0, s, r, coef = state
@@ -407,31 +429,70 @@ def cpu_pass(state):
         t.grad = None
     v = v0.clone().requires_grad_(True)
     ed = e0.clone().requires_grad_(True)
-    out = orc.processor(w, "sum", "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
+    out = orc.processor(w, aggregator, "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
     loss = (out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3
     loss.backward()
     return float(loss)
 
 
-def cpu_state():
-    from hgn_b200 import synthetic
+def cpu_state(sample=None, aggregator="sum"):
     torch.set_num_threads(os.cpu_count() or 1)
-    data = build_inputs(CPU_SAMPLE_W, CPU_SAMPLE_H, CPU_SAMPLE_LAYERS)
+    w_, h_, batch, layers = sample or (CPU_SAMPLE_W, CPU_SAMPLE_H, 1, CPU_SAMPLE_LAYERS)
+    data = build_inputs(w_, h_, layers, aggregator=aggregator, batch=batch)
     w = {k: t.clone().requires_grad_(True) for k, t in data["weights"].items()}
     return (w, data["v0"], data["e0"], data["senders"], data["receivers"], data["coef_v"]), data["e"]
 
 
-def cpu_baseline(steps=1):
-    state, e = cpu_state()
-    cpu_pass(state)                      # untimed: first touch / thread pool start
+def cpu_baseline(steps=1, sample=None, aggregator="sum"):
+    w_, h_, batch, layers = sample or (CPU_SAMPLE_W, CPU_SAMPLE_H, 1, CPU_SAMPLE_LAYERS)
+    state, e = cpu_state(sample, aggregator)
+    cpu_pass(state, aggregator)          # untimed: first touch / thread pool start
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pass(state)
+        cpu_pass(state, aggregator)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": e * CPU_SAMPLE_LAYERS / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": e * layers / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "seconds_per_pass": dt,
-            "sample": f"{CPU_SAMPLE_W}x{CPU_SAMPLE_H} sub-mesh of the workload ({e} directed edges), {CPU_SAMPLE_LAYERS} layer, "
+            "sample": f"{w_}x{h_}" + (f" x {batch}" if batch > 1 else "") + f" mesh of the workload ({e} directed edges), {layers} layer(s), {aggregator}, "
                       "fwd+bwd, fp32, oracle/hgn_oracle.py (torch CPU ops = the reference's own arithmetic)"}
+
+
+def torch_cuda_reference(dev, data, aggregator, layers):
+    """Same-box torch path: the reference's arithmetic (the oracle port: index_select / cat / addmm / relu /
+    layer_norm / scatter_add through autograd, fp32 features, int64 indices) on the B200 through torch's own CUDA kernels, on the
+    workload's full mesh.  A baseline beside the number, like `cpu_baseline`; none of hgn_b200's kernels run here."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgn_oracle as orc
+    keep = tuple(f"processor.graphnet_blocks.{i}." for i in range(layers))
+    w = {k: t.to(dev).requires_grad_(True) for k, t in data["weights"].items() if k.startswith(keep)}
+    v0, e0, coef = data["v0"].to(dev), data["e0"].to(dev), data["coef_v"].to(dev)
+    s, r = data["senders"].to(dev), data["receivers"].to(dev)
+
+    def one():
+        for t in w.values():
+            t.grad = None
+        v = v0.clone().requires_grad_(True)
+        ed = e0.clone().requires_grad_(True)
+        out = orc.processor(w, aggregator, "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
+        ((out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3).backward()
+
+    try:
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            one()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        return {"value": data["e"] * layers / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms, "kind": "port on torch CUDA ops",
+                "sample": f"the workload's full mesh ({data['e']} directed edges), {layers} layer(s), {aggregator}, fwd+bwd, fp32, "
+                          "oracle/hgn_oracle.py on cuda:0 (torch eager kernels: cuBLAS addmm, scatter_add atomics)"}
+    except Exception as exc:                    # e.g. out of memory: a baseline, never fatal to the bench line
+        return {"value": None, "error": f"{type(exc).__name__}: {exc}"[:200]}
 
 
 def run_reference(args):
@@ -466,8 +527,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--aggregator", default="sum", choices=["sum", "pna"],
-                    help="message-passing aggregator (the headline metric is quoted on 'sum'; 'pna' is the reference configs' default)")
+    ap.add_argument("--aggregator", default=None, choices=["sum", "pna"],
+                    help="message-passing aggregator (default: the workload's; the headline metric is quoted on 'sum'; 'pna' is the "
+                         "reference configs' default)")
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS),
+                    help="cfg5 = the headline 1M/6M mesh (the bench line); cfg2 / cfg4 = small-mesh batched training shapes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

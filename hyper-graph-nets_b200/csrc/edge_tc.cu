@@ -455,9 +455,8 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 64; ++j) pq[j] = 0u;
         if (ld_on) load_tables(si, ri, pq);
-        if (t > 0) {
-          wait_cs(1, t - 1);                                    // the producers' dH2' column sum has left this buffer
-          if (tid == 0) { tma_store_wait_read<0>(); mbar_arrive(&bars[kEbDeFree]); }   // ... and so has the TMA store of d e
+        if (t > 0) {                                            // the TMA store of d e has read this buffer
+          if (tid == 0) { tma_store_wait_read<0>(); mbar_arrive(&bars[kEbDeFree]); }
           mbar_wait(&bars[kEbDeFree], uint32_t(t - 1) & 1, 73);
         }
         wait_acc(100); if (tid == 0) stamp(a, t, 10);
@@ -668,7 +667,9 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           o[j] = pack_bf16(x0.x, x0.y);
           o[16 + j] = pack_bf16(x1.x, x1.y);
         }
-        // staged in buffer B (dH2' is dead: the chain commit above came after the dW1 MMAs) and stored by the producers' TMA
+        // staged in buffer B (dH2' is dead: the chain commit above came after the dW1 MMAs, and the producers' column sum of it,
+        // long finished, is awaited here rather than assumed) and stored by TMA
+        wait_cs(1, t);
         store_row(B, o);
         fence_async_smem();
         __syncwarp(); if (lane == 0) mbar_arrive(&bars[kEbDe]);

@@ -14,7 +14,7 @@ HGN_F32 = 0
 HGN_BF16 = 1
 AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN = 1, 2, 4, 8
 HGN_MAX_CHUNKS = 24
-ABI_VERSION = 2            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
+ABI_VERSION = 3            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhgn_b200.so")
 
@@ -60,6 +60,11 @@ SIGNATURES = {
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hgn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "hgn_world_edges_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "hgn_world_edges_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, ctypes.c_float, c_int32, c_int32,
+                                      c_void_p, c_size_t, POINTER(c_int64), c_void_p]),
+    "hgn_world_edges_emit": (c_int, [c_void_p, c_void_p, c_int64, c_int64, ctypes.c_float, c_int32, c_void_p, c_size_t,
+                                     c_void_p, c_void_p, c_int64, c_void_p]),
     "hgn_profile_enable": (c_int, [c_int]),
     "hgn_profile_reset": (c_int, []),
     "hgn_profile_report": (c_size_t, [c_char_p, c_size_t]),

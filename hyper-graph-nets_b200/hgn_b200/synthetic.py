@@ -88,6 +88,37 @@ def box_tetrahedra(nx: int, ny: int, nz: int) -> np.ndarray:
     return np.asarray(cells, np.int32)
 
 
+def plate_frame(plate=(9, 9, 2), obstacle=(4, 4, 2), spacing: float = 0.02, gap: float = 0.012, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Two-body deforming-plate frame in one index space (cfg 3): a NORMAL plate lattice (its first lattice column
+    HANDLE) and an OBSTACLE block hovering `gap` above it, the obstacle nodes contiguous at the end
+    (src/rmp/remote_message_passing.py:82-137 requires that).  Tetrahedral cells, seeded jitter; spacing and gap are chosen so
+    that mesh neighbours, plate-obstacle pairs and some non-edges all lie around the 0.03 world-edge radius (plate.py:87)."""
+    rng = np.random.default_rng(seed)
+
+    def lattice(dims, origin):
+        nx, ny, nz = dims
+        k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        return np.stack([i, j, k], -1).reshape(-1, 3).astype(np.float32) * np.float32(spacing) + np.asarray(origin, np.float32)
+
+    p_pos = lattice(plate, (0.0, 0.0, 0.0))
+    o_pos = lattice(obstacle, (2.3 * spacing, 1.7 * spacing, (plate[2] - 1) * spacing + gap))
+    n_plate = p_pos.shape[0]
+    mesh_pos = np.concatenate([p_pos, o_pos], 0)
+    world_pos = mesh_pos + rng.normal(0.0, 0.1 * spacing, mesh_pos.shape).astype(np.float32)
+    target = world_pos + rng.normal(0.0, 0.001, mesh_pos.shape).astype(np.float32)
+    node_type = np.zeros((mesh_pos.shape[0], 1), np.int32)
+    node_type[:n_plate][np.arange(n_plate) % plate[0] == 0, 0] = 3   # HANDLE
+    node_type[n_plate:, 0] = 1                                     # OBSTACLE
+    cells = np.concatenate([box_tetrahedra(*plate), box_tetrahedra(*obstacle) + n_plate], 0).astype(np.int32)
+    return {
+        "cells": torch.from_numpy(cells),
+        "mesh_pos": torch.from_numpy(mesh_pos.astype(np.float32)),
+        "world_pos": torch.from_numpy(world_pos.astype(np.float32)),
+        "target|world_pos": torch.from_numpy(target.astype(np.float32)),
+        "node_type": torch.from_numpy(node_type),
+    }
+
+
 # ----------------------------------------------------------------------------------------------
 # deterministic tensors
 # ----------------------------------------------------------------------------------------------

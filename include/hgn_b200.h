@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HGN_B200_ABI_VERSION 2
+#define HGN_B200_ABI_VERSION 3
 
 typedef enum {
   HGN_OK = 0,
@@ -213,6 +213,25 @@ int hgn_colsum(int dtype, const void* x, int64_t rows, int32_t D, float* out,
 int hgn_rows_gather(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst, void* stream);
 int hgn_rows_scatter(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst,
                      int accumulate, void* stream);
+
+/* ---- world edges: fixed-radius neighbour search ----------------------------------------------------
+ * Replaces the dense search of PlateModel.build_graph (src/model/plate.py:86-110): torch.cdist over all
+ * node pairs, `< radius`, diagonal and existing mesh edges removed, senders restricted to sender_type
+ * (OBSTACLE) and receivers to receiver_type (NORMAL), then torch.nonzero.  A uniform-grid cell list gives
+ * the identical (sender, receiver) list in torch.nonzero's row-major order, int64, with the distance
+ * evaluated in torch.cdist's own fp32 arithmetic (see csrc/world_edges.cu).  world_pos is [N,3] fp32,
+ * node_type [N] int32, mesh_senders / mesh_receivers the reference's int64 two-way mesh edges.
+ * Two calls because the output size is data dependent (torch.nonzero synchronises for the same reason):
+ * _count fills the workspace, synchronises the stream and returns the number of pairs in *host_num_pairs;
+ * _emit writes them from the same (unmodified) workspace and inputs. */
+size_t hgn_world_edges_workspace_bytes(int64_t num_nodes, int64_t num_mesh_edges);
+int hgn_world_edges_count(const float* world_pos, const int32_t* node_type, int64_t num_nodes,
+                          const int64_t* mesh_senders, const int64_t* mesh_receivers, int64_t num_mesh_edges,
+                          float radius, int32_t sender_type, int32_t receiver_type,
+                          void* workspace, size_t workspace_bytes, int64_t* host_num_pairs, void* stream);
+int hgn_world_edges_emit(const float* world_pos, const int32_t* node_type, int64_t num_nodes, int64_t num_mesh_edges,
+                         float radius, int32_t sender_type, const void* workspace, size_t workspace_bytes,
+                         int64_t* senders_out, int64_t* receivers_out, int64_t capacity, void* stream);
 
 /* ---- kernel timing (tracing hook; the reference only has wall-clock time.time() around a batch,
  * src/algorithms/MeshSimulator.py:135-155) ----------------------------------------------------------

@@ -68,11 +68,11 @@ class _SegmentArgReduce(torch.autograd.Function):
         E = data.shape[0]
         tail = tuple(data.shape[1:])
         idx = seg.view((E,) + (1,) * len(tail)).expand_as(data)
-        out = torch.zeros((num_segments,) + tail, dtype=data.dtype)
+        out = torch.zeros((num_segments,) + tail, dtype=data.dtype, device=data.device)
         out.scatter_reduce_(0, idx, data, "amax" if is_max else "amin", include_self=False)
-        pos = torch.arange(E, dtype=torch.int64).view((E,) + (1,) * len(tail)).expand_as(data)
+        pos = torch.arange(E, dtype=torch.int64, device=data.device).view((E,) + (1,) * len(tail)).expand_as(data)
         cand = torch.where(data == out.gather(0, idx), pos, torch.full_like(pos, E))
-        arg = torch.full(out.shape, E, dtype=torch.int64)
+        arg = torch.full(out.shape, E, dtype=torch.int64, device=data.device)
         arg.scatter_reduce_(0, idx, cand, "amin", include_self=True)
         ctx.save_for_backward(arg)
         ctx.E = E
@@ -81,7 +81,7 @@ class _SegmentArgReduce(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (arg,) = ctx.saved_tensors
-        buf = torch.zeros((ctx.E + 1,) + tuple(g.shape[1:]), dtype=g.dtype)
+        buf = torch.zeros((ctx.E + 1,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
         buf.scatter_(0, arg, g)
         return buf[: ctx.E], None, None, None
 
@@ -107,9 +107,9 @@ def segment_reduce(data: torch.Tensor, segment_ids: torch.Tensor, num_segments: 
     tail = tuple(x.shape[1:])
     idx = seg.view((E,) + (1,) * len(tail)).expand_as(x)
     if operation == "sum":
-        out = torch.zeros((num_segments,) + tail, dtype=x.dtype).scatter_add(0, idx, x)
+        out = torch.zeros((num_segments,) + tail, dtype=x.dtype, device=x.device).scatter_add(0, idx, x)
     elif operation == "mean":
-        total = torch.zeros((num_segments,) + tail, dtype=x.dtype).scatter_add(0, idx, x)
+        total = torch.zeros((num_segments,) + tail, dtype=x.dtype, device=x.device).scatter_add(0, idx, x)
         count = torch.bincount(seg, minlength=num_segments).clamp(min=1).to(x.dtype)
         out = total / count.view((-1,) + (1,) * len(tail))
     elif operation == "max":
@@ -119,8 +119,8 @@ def segment_reduce(data: torch.Tensor, segment_ids: torch.Tensor, num_segments: 
     elif operation == "std":
         count = torch.bincount(seg, minlength=num_segments).to(x.dtype)
         shape1 = (-1,) + (1,) * len(tail)
-        mean = torch.zeros((num_segments,) + tail, dtype=x.dtype).scatter_add(0, idx, x) / count.clamp(min=1).view(shape1)
-        var = torch.zeros((num_segments,) + tail, dtype=x.dtype).scatter_add(0, idx, (x - mean.gather(0, idx)) ** 2)
+        mean = torch.zeros((num_segments,) + tail, dtype=x.dtype, device=x.device).scatter_add(0, idx, x) / count.clamp(min=1).view(shape1)
+        var = torch.zeros((num_segments,) + tail, dtype=x.dtype, device=x.device).scatter_add(0, idx, (x - mean.gather(0, idx)) ** 2)
         out = (var / ((count - 1).clamp(min=1).view(shape1) + 1e-6)).sqrt()
     else:
         raise Exception("Invalid operation type!")
@@ -347,3 +347,22 @@ def triangles_to_edges(faces: torch.Tensor, deform: bool = False):
     s = uniq[:, 0].to(torch.int64)
     r = uniq[:, 1].to(torch.int64)
     return {"two_way_connectivity": (torch.cat((s, r)), torch.cat((r, s))), "senders": s, "receivers": r}
+
+
+# ----------------------------------------------------------------------------------------------
+# world edges of the deforming-plate graph  (src/model/plate.py:86-110)
+# ----------------------------------------------------------------------------------------------
+def world_edges(world_pos: torch.Tensor, node_type: torch.Tensor, mesh_senders: torch.Tensor, mesh_receivers: torch.Tensor,
+                radius: float = 0.03, obstacle: int = 1, normal: int = 0):
+    """Dense restatement, statement by statement: ``torch.cdist`` matrix, ``< radius``, diagonal cleared, existing mesh edges
+    cleared, rows that are not OBSTACLE nodes and columns that are not NORMAL nodes cleared, ``torch.nonzero``.
+    ``node_type`` is the reference's ``[N, 1]`` tensor (or ``[N]``).  O(N^2) memory: small cases only."""
+    types = node_type.reshape(-1)
+    dist = torch.cdist(world_pos, world_pos, p=2)
+    conn = torch.where(dist < radius, True, False)
+    conn = conn.fill_diagonal_(False)
+    conn[mesh_senders, mesh_receivers] = False
+    conn[torch.ne(types, obstacle), :] = False
+    conn[:, torch.ne(types, normal)] = False
+    senders, receivers = torch.nonzero(conn, as_tuple=True)
+    return senders, receivers

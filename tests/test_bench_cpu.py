@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import torch  # noqa: E402
 import bench  # noqa: E402
 
 
@@ -42,3 +43,15 @@ def test_roofline_accounting_of_the_projected_kernels():
     assert bench.dominant_kernel_roofline(kernels, 1, 1000, 100, peaks)["traffic"] is None
     seg = bench.dominant_kernel_roofline([{"name": "segment_reduce", "launches": 3, "ms": 0.93}], 1, e, n, peaks)
     assert seg["bound"] == "hbm" and abs(seg["achieved"] - ((e + n) * 256 + e * 4) / 0.31e-3 / 1e9) < 1e-6
+
+
+def test_batched_workload_is_disjoint_copies_of_the_mesh():
+    # MeshSimulator._get_batched (src/algorithms/MeshSimulator.py:196-217): graph i's indices are offset by i * N
+    one = bench.build_inputs(5, 4, 1)
+    three = bench.build_inputs(5, 4, 1, batch=3, aggregator="pna")
+    n, e = one["n"], one["e"]
+    assert three["n"] == 3 * n and three["e"] == 3 * e and three["v0"].shape == (3 * n, 128)
+    for i in range(3):
+        assert torch.equal(three["senders"][i * e:(i + 1) * e], one["senders"] + i * n)
+        assert torch.equal(three["receivers"][i * e:(i + 1) * e], one["receivers"] + i * n)
+    assert set(bench.WORKLOADS) == {"cfg2", "cfg4", "cfg5"} and bench.WORKLOADS["cfg5"][:5] == (1000, 1000, 1, 15, "sum")

@@ -1,0 +1,131 @@
+"""World-edge cell-list kernels (csrc/world_edges.cu, through the C ABI) vs the golden vectors of the live reference, vs the dense
+oracle on seeded random two-body clouds, and -- at 1 M nodes -- through size-independent properties and a blocked dense check."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "hyper-graph-nets_b200"))
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "world_edges.npz"))
+
+
+def _ours(pos, types, ms, mr, **kw):
+    from hgn_b200.world_edges import world_edges
+    s, r = world_edges(pos.cuda(), types.cuda(), ms.cuda(), mr.cuda(), **kw)
+    assert s.dtype == torch.int64 and r.dtype == torch.int64 and s.is_cuda
+    return s.cpu(), r.cpu()
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_matches_reference_golden(case):
+    pos = torch.from_numpy(GOLD[f"{case}_world_pos"])
+    types = torch.from_numpy(GOLD[f"{case}_node_type"])
+    ms = torch.from_numpy(GOLD[f"{case}_mesh_edges_senders"])
+    mr = torch.from_numpy(GOLD[f"{case}_mesh_edges_receivers"])
+    s, r = _ours(pos, types, ms, mr)
+    assert np.array_equal(s.numpy(), GOLD[f"{case}_world_edges_senders"])
+    assert np.array_equal(r.numpy(), GOLD[f"{case}_world_edges_receivers"])
+
+
+def _cloud(n, seed, offset=0.0, extent=(0.6, 0.5, 0.12)):
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.rand(n, 3, generator=g) * torch.tensor(extent) + offset
+    types = torch.tensor([0, 0, 0, 1, 1, 3])[torch.randint(0, 6, (n,), generator=g)].to(torch.int32).reshape(-1, 1)
+    # "mesh edges": random pairs plus every 3rd close OBSTACLE -> NORMAL pair (those must be removed from the world edges)
+    ms = torch.randint(0, n, (4 * n,), generator=g)
+    mr = torch.randint(0, n, (4 * n,), generator=g)
+    return pos.float(), types, ms, mr
+
+
+@pytest.mark.parametrize("n,seed,offset", [(3000, 0, 0.0), (5000, 1, 0.0), (2500, 2, 5.0), (257, 3, -2.0), (40, 4, 0.0)])
+def test_matches_dense_oracle_on_random_clouds(n, seed, offset):
+    import hgn_oracle as orc
+    pos, types, ms, mr = _cloud(n, seed, offset)
+    s0, r0 = orc.world_edges(pos, types, ms, mr)
+    close = s0[::3], r0[::3]                                    # put a third of the true world edges into the mesh edge list
+    ms, mr = torch.cat([ms, close[0]]), torch.cat([mr, close[1]])
+    s_ref, r_ref = orc.world_edges(pos, types, ms, mr)
+    assert n < 100 or (s_ref.numel() > 0 and s_ref.numel() < s0.numel())
+    s, r = _ours(pos, types, ms, mr)
+    assert torch.equal(s, s_ref) and torch.equal(r, r_ref)
+    s2, r2 = _ours(pos, types, ms, mr)                          # run-to-run identical
+    assert torch.equal(s, s2) and torch.equal(r, r2)
+
+
+def test_other_radius_and_types():
+    import hgn_oracle as orc
+    pos, types, ms, mr = _cloud(2000, 7)
+    s_ref, r_ref = orc.world_edges(pos, types, ms, mr, radius=0.05, obstacle=3, normal=1)
+    s, r = _ours(pos, types, ms, mr, radius=0.05, sender_type=3, receiver_type=1)
+    assert s_ref.numel() > 0 and torch.equal(s, s_ref) and torch.equal(r, r_ref)
+
+
+def test_degenerate_inputs():
+    e = torch.zeros(0, dtype=torch.int64)
+    s, r = _ours(torch.zeros(0, 3), torch.zeros(0, 1, dtype=torch.int32), e, e)
+    assert s.numel() == 0 and r.numel() == 0
+    pos = torch.rand(100, 3) * 0.05
+    for t in (0, 1):                                            # only receivers / only senders
+        s, r = _ours(pos, torch.full((100, 1), t, dtype=torch.int32), e, e)
+        assert s.numel() == 0
+    # all nodes at one point: every OBSTACLE -> NORMAL pair is an edge, ordered row-major
+    types = torch.tensor([1, 0, 0, 1, 3, 0], dtype=torch.int32)
+    s, r = _ours(torch.ones(6, 3), types, e, e)
+    assert s.tolist() == [0, 0, 0, 3, 3, 3] and r.tolist() == [1, 2, 5, 1, 2, 5]
+    # non-finite coordinates connect to nothing (cdist gives nan, `nan < radius` is False)
+    pos = torch.ones(6, 3); pos[1, 0] = float("nan"); pos[3, 2] = float("inf")
+    s, r = _ours(pos, types, e, e)
+    assert s.tolist() == [0, 0] and r.tolist() == [2, 5]
+    from hgn_b200 import _cabi
+    with pytest.raises(_cabi.HgnError):
+        _ours(torch.ones(6, 3), types, e, e, radius=-1.0)
+
+
+def test_million_node_plate_properties_and_blocked_dense_check():
+    # 1000 x 1000 plate lattice (NORMAL, first column HANDLE) with a 120 x 120 OBSTACLE patch hovering above it
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    i, j = torch.meshgrid(torch.arange(1000), torch.arange(1000), indexing="ij")
+    plate = torch.stack([i.reshape(-1) * 0.02, j.reshape(-1) * 0.02, torch.zeros(10 ** 6)], -1)
+    oi, oj = torch.meshgrid(torch.arange(120), torch.arange(120), indexing="ij")
+    obst = torch.stack([oi.reshape(-1) * 0.02 + 7.013, oj.reshape(-1) * 0.02 + 3.007, torch.full((14400,), 0.015)], -1)
+    pos = torch.cat([plate, obst]).float()
+    pos = pos + (torch.rand(pos.shape, generator=g) - 0.5) * 0.004
+    types = torch.zeros(pos.shape[0], dtype=torch.int32)
+    types[:10 ** 6][torch.arange(10 ** 6) % 1000 == 0] = 3
+    types[10 ** 6:] = 1
+    n = pos.shape[0]
+    ms = torch.arange(n - 1); mr = ms + 1                       # a chain of "mesh edges"; one of them joins plate and obstacle
+    from hgn_b200.world_edges import world_edges
+    pos_d, types_d = pos.to(dev), types.to(dev)
+    s, r = world_edges(pos_d, types_d, ms.to(dev), mr.to(dev))
+    assert s.numel() > 50000
+    assert bool((types_d[s] == 1).all()) and bool((types_d[r] == 0).all())
+    key = s * n + r
+    assert bool((key[1:] > key[:-1]).all())                     # sorted row-major, no duplicates
+    # the reference's distance is the cancellation-prone |x|^2 + |y|^2 - 2 x.y in fp32: at |x|^2 ~ 600 its rounding error is of the
+    # order of radius^2 itself, so pairs a little beyond the radius are connected (faithfully); the bound is the kernel's own margin
+    d2 = (pos_d[s].double() - pos_d[r].double()).pow(2).sum(-1)
+    e2 = 16 * 2.0 ** -24 * float(pos_d.double().pow(2).sum(-1).max())
+    assert float(d2.max()) < 0.03 ** 2 + 2 * e2 and float(d2.min()) < 0.03 ** 2
+    # blocked dense check with torch's own cdist on the device (the reference's formula through cuBLAS), obstacle rows only
+    normal = types_d == 0
+    total, got = 0, []
+    for lo in range(10 ** 6, n, 1800):
+        rows = torch.arange(lo, min(lo + 1800, n), device=dev)
+        dist = torch.cdist(pos_d[rows], pos_d, p=2, compute_mode="use_mm_for_euclid_dist")
+        conn = (dist < 0.03) & normal[None, :]
+        rr, cc = torch.nonzero(conn, as_tuple=True)
+        got.append(torch.stack([rows[rr], cc], 1))
+        total += rr.numel()
+        del dist, conn
+    ref = torch.cat(got)
+    assert total == s.numel()
+    assert torch.equal(ref[:, 0], s) and torch.equal(ref[:, 1], r)
