@@ -75,4 +75,20 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Sum over `parts` values `stride` apart in their original order (p = 0, 1, 2, ...: bitwise the sequential sum), with the loads of
+// eight parts in flight at a time -- the dependent load-add chain made these reductions latency-bound (64 us for 148 parts).
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ src, int parts, int64_t stride) {
+  float s = 0.f;
+  int p = 0;
+  for (; p + 8 <= parts; p += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(src + int64_t(p + k) * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; p < parts; ++p) s += __ldg(src + int64_t(p) * stride);
+  return s;
+}
+
 }  // namespace hgn

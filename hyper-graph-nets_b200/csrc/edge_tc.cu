@@ -730,21 +730,17 @@ __global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, cons
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * kD * kD) {
     if (skip_we && i < kD * kD) return;          // dWe comes from the streaming weight-gradient kernel
-    float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += w_partial[int64_t(p) * 3 * kD * kD + i];
+    const float s = ordered_sum(w_partial + i, parts, int64_t(3) * kD * kD);
     const int z = i / (kD * kD), o = (i / kD) % kD, c = i % kD;
     if (z == 0) gW0[(int64_t(o) * w0_chunks + w0_chunk0) * kD + c] = s;
     else if (z == 1) gW1[o * kD + c] = s;
     else gW2[o * kD + c] = s;
   } else if (i < 3 * kD * kD + 5 * kD) {
     const int k = (i - 3 * kD * kD) / kD, c = i % kD;
-    float s = 0.f;
     if (k < 3) {
-      for (int p = 0; p < parts; ++p) s += prod_colpart[(int64_t(p) * 3 + k) * kD + c];
-      (k == 0 ? gb2 : k == 1 ? gb1 : gb0)[c] = s;
+      (k == 0 ? gb2 : k == 1 ? gb1 : gb0)[c] = ordered_sum(prod_colpart + int64_t(k) * kD + c, parts, int64_t(3) * kD);
     } else {
-      for (int p = 0; p < parts * 4; ++p) s += epi_colpart[(int64_t(p) * 2 + (k - 3)) * kD + c];
-      (k == 3 ? gbeta : ggamma)[c] = s;
+      (k == 3 ? gbeta : ggamma)[c] = ordered_sum(epi_colpart + int64_t(k - 3) * kD + c, parts * 4, int64_t(2) * kD);
     }
   }
 }
@@ -753,9 +749,7 @@ __global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, cons
 __global__ void reduce_w0_block_kernel(const float* __restrict__ partial, int parts, int n_z, int z, float* __restrict__ gW0, int ld, int col0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kD * kD) return;
-  float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partial[(int64_t(p) * n_z + z) * kD * kD + i];
-  gW0[int64_t(i / kD) * ld + col0 + (i % kD)] = s;
+  gW0[int64_t(i / kD) * ld + col0 + (i % kD)] = ordered_sum(partial + int64_t(z) * kD * kD + i, parts, int64_t(n_z) * kD * kD);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------

@@ -473,9 +473,7 @@ mlp_wgrad_f32_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int rows_pe
 __global__ void reduce_parts_kernel(const float* __restrict__ in, int parts, int64_t stride, int64_t n, float* __restrict__ out) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
-  float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += in[int64_t(p) * stride + i];
-  out[i] = s;
+  out[i] = ordered_sum(in + i, parts, stride);
 }
 // dW0[o][c*128 + i] = sum_p partial[p][z=c][o][i]
 __global__ void reduce_w0_kernel(const float* __restrict__ partial, int parts, int n_z, int n_chunks, float* __restrict__ dW0) {
@@ -484,9 +482,7 @@ __global__ void reduce_w0_kernel(const float* __restrict__ partial, int parts, i
   if (i >= kD * k0) return;
   const int64_t o = i / k0, col = i - o * k0;
   const int c = int(col / kD), ii = int(col - int64_t(c) * kD);
-  float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partial[((int64_t(p) * n_z + c) * kD + o) * kD + ii];
-  dW0[i] = s;
+  dW0[i] = ordered_sum(partial + (int64_t(c) * kD + o) * kD + ii, parts, int64_t(n_z) * kD * kD);
 }
 
 // partial layout [parts][n_chunks + 2][128][128]: z < n_chunks -> W0 chunk z ; n_chunks -> W1 ; n_chunks + 1 -> W2

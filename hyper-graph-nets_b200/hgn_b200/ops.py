@@ -146,7 +146,10 @@ def _pack_weights(cache: dict, dtype: torch.dtype, n_chunks: int, params: Sequen
     key = (dtype, n_chunks)
     versions = tuple((p.data_ptr(), p._version) for p in params)
     hit = cache.get(key)
-    if hit is not None and hit[0] == versions:
+    # While a CUDA graph is being captured the pack kernel always becomes part of the graph: a replay must re-read the master
+    # weights the (captured) optimizer step has changed, and the host-side version check does not run at replay time.
+    capturing = torch.cuda.is_current_stream_capturing()
+    if hit is not None and hit[0] == versions and not capturing:
         return hit[1]
     lib = _cabi.load()
     code = _cabi.dtype_code(dtype)
@@ -156,7 +159,8 @@ def _pack_weights(cache: dict, dtype: torch.dtype, n_chunks: int, params: Sequen
         raise _cabi.HgnError("MLP parameters must be float32 (master weights)")
     _cabi.check(lib.hgn_mlp_pack(code, n_chunks, *[p.data_ptr() for p in ps], blob.data_ptr(), _cabi.stream_ptr()), "hgn_mlp_pack")
     _count()
-    cache[key] = (versions, blob)
+    if not capturing:
+        cache[key] = (versions, blob)
     return blob
 
 
