@@ -141,7 +141,7 @@ def make_processor(weights, layers, precision, device, aggregator="sum"):
 
 
 def run_ours(args):
-    from hgn_b200 import _cabi, ops
+    from hgn_b200 import _cabi, ops, partition
     from hgn_b200.util import EdgeSet, MultiGraph
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -151,7 +151,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and args.workload == "cfg5":
         from hgn_b200 import partition
         args.aggregator = args.aggregator or "sum"
         return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler,
@@ -159,7 +159,9 @@ def run_ours(args):
 
     gw, gh, batch, layers, default_agg, cpu_sample, wl_text = WORKLOADS[args.workload]
     args.aggregator = args.aggregator or default_agg
-    data = build_inputs(gw, gh, layers, aggregator=args.aggregator, batch=batch)
+    # world > 1 with a small-mesh workload: trajectory data parallelism (BASELINE.json configs[3]) -- every rank a
+    # replica with its own batch (seed = rank), one flat fp32 gradient all-reduce per step, weak scaling
+    data = build_inputs(gw, gh, layers, seed=rank, aggregator=args.aggregator, batch=batch)
     n, e = data["n"], data["e"]
     f_node = 2 * ((1 + (4 if args.aggregator == "pna" else 1)) + 2) * LATENT * LATENT
     proc = make_processor(data["weights"], layers, "bf16", dev, args.aggregator)
@@ -179,7 +181,21 @@ def run_ours(args):
         out = proc(MultiGraph([v], [EdgeSet("mesh_edges", ed, senders, receivers)]))
         loss = (out.node_features[0] * coef_v).sum() + out.edge_sets[0].features.sum() * 1e-3
         loss.backward()
+        if world > 1:
+            partition.allreduce_gradients(proc)
         return loss
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     def step_resident():
         return step(v_dev.detach(), e_dev.detach())
@@ -211,40 +227,40 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    torch.cuda.synchronize()
+    fence()
 
     # ---- timed region: inputs resident in HBM --------------------------------------------------------
     _cabi.profile(True)
     launches0 = ops.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
+        fence()
         start.record()
         for _ in range(args.steps):
             step_resident()
         stop.record()
-        torch.cuda.synchronize()
-    ms_per_step = start.elapsed_time(stop) / args.steps
+        fence()
+    ms_per_step = max_over_ranks(start.elapsed_time(stop) / args.steps)
     launches = ops.launch_count - launches0
     kernels = _cabi.profile_report()
     _cabi.profile(False)
-    value = e * layers / (ms_per_step * 1e-3)
+    value = e * layers * world / (ms_per_step * 1e-3)
 
     # ---- end to end: pinned host inputs -> H2D -> fwd+bwd -> D2H loss ---------------------------------
     run_e2e(3)                                  # warm-up: two input sets are alive at a time, let the allocator cache both
-    torch.cuda.synchronize()
+    fence()
     e2e_steps = max(2, min(args.steps, 8))
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()                                 # on the compute stream, which waits for every copy it consumes
     run_e2e(e2e_steps)
     t1.record()
-    torch.cuda.synchronize()
-    e2e_ms = t0.elapsed_time(t1) / e2e_steps
-    e2e_value = e * layers / (e2e_ms * 1e-3)
+    fence()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1) / e2e_steps)
+    e2e_value = e * layers * world / (e2e_ms * 1e-3)
 
     # ---- small meshes: the same resident step (forward + backward) captured in ONE CUDA graph -------------
     graphed = None
-    if args.workload != "cfg5":
+    if args.workload != "cfg5" and world == 1:
         graphed = graphed_step(step_resident, params, args.steps, e * layers)
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------
@@ -252,20 +268,25 @@ def run_ours(args):
     roofline = dominant_kernel_roofline(kernels, args.steps, e, n, peaks)
 
     # ---- CPU baseline: oracle port on a bounded sub-mesh ------------------------------------------------
-    cpu = cpu_baseline(steps=1, sample=cpu_sample, aggregator=args.aggregator)
+    cpu = cpu_baseline(steps=1, sample=cpu_sample, aggregator=args.aggregator) if world == 1 else None
+    if rank != 0:
+        dist.barrier()
+        return
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": f"synthetic (seeded {gw}x{gh} triangulated grid" + (f" x {batch}" if batch > 1 else "") + ", seeded weights)",
         "config": {"workload": f"{wl_text}, {layers} GraphNet layers, {args.aggregator} aggregator, "
                                "processor fwd+bwd", "nodes": n, "edges": e, "layers": layers, "latent": LATENT,
                    "l2_policy": ("inputs larger than L2 (1.8 GB of bf16 latents per layer)" if args.workload == "cfg5" else
                                  "small mesh: the whole step's working set is L2-resident by construction (launch-bound shape)"),
-                   "partitioning": "none", "backward": ops.backward_mode},
+                   "partitioning": "none", "backward": ops.backward_mode,
+                   "parallelism": (f"dp{world}: one replica and one batch (seed = rank) per GPU, one flat fp32 gradient all-reduce (NCCL) per "
+                                   "step; value = all ranks' edge updates / max-over-ranks time") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "pipeline": "H2D of step i+1 on a copy stream overlaps step i; loss D2H + stream sync every step",
-                "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(v0_host.numel() * 4 + e0_host.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
@@ -279,11 +300,13 @@ def run_ours(args):
         line["cuda_graph"] = graphed
     if args.workload == "cfg5" and args.aggregator == "sum" and not os.environ.get("HGN_BENCH_NO_ROLLOUT"):
         line["rollout"] = rollout_bench(dev)         # the metric's second half, BASELINE.json configs[1]
-    if not os.environ.get("HGN_BENCH_NO_TORCH_REFERENCE"):
+    if world == 1 and not os.environ.get("HGN_BENCH_NO_TORCH_REFERENCE"):
         del proc, params, v_dev, e_dev
         torch.cuda.empty_cache()
         line["torch_cuda_reference"] = torch_cuda_reference(dev, data, args.aggregator, layers if args.workload != "cfg5" else 1)
     print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
 
 
 def graphed_step(step_fn, params, steps, edge_updates_per_step):

@@ -91,3 +91,55 @@ def test_rollout_error_curve_vs_oracle():
         curve = [float((a - b).norm() / (b - x0).norm().clamp_min(1e-12)) for a, b in zip(ours, ref)]
         print(f"rollout error curve [{precision}]: " + " ".join(f"{c:.2e}" for c in curve))
         assert max(curve) <= TOL[precision], f"{precision}: rollout error {max(curve):.3e} > {TOL[precision]:g} (curve {curve})"
+
+
+@pytest.mark.gpu
+def test_graphed_training_step_equals_eager_including_the_optimizer():
+    """fwd + bwd + SGD step captured in one CUDA graph (hgn_b200.graphed.GraphedStep) == the same three eager steps, bit for bit:
+    the kernels are deterministic and the weight-pack kernels are part of the graph, so replays see the updated weights."""
+    import copy
+    from hgn_b200 import synthetic
+    from hgn_b200.graphed import GraphedStep
+    from hgn_b200.migration.meshgraphnet import MeshGraphNet
+    from hgn_b200.util import EdgeSet, MultiGraph
+    dev = torch.device("cuda")
+    s, r = (t.to(dev) for t in synthetic.grid_edges_two_way(20, 12))
+    n, e = 240, s.numel()
+    torch.manual_seed(1)
+    batches = [(torch.randn(n, 5, device=dev), torch.randn(e, 7, device=dev), torch.randn(n, 3, device=dev)) for _ in range(3)]
+    results = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        model = MeshGraphNet(3, 128, 2, "sum", 3, "none", ["mesh_edges"]).to(dev)
+        model.processor.precision = "bf16"
+        nf, ef, tgt = (t.clone() for t in batches[0])
+        with torch.no_grad():
+            model(MultiGraph([nf], [EdgeSet("mesh_edges", ef, s, r)]))            # materialise the lazy parameters
+        params = list(model.parameters())
+        opt = torch.optim.SGD(params, lr=1e-2)
+        start = copy.deepcopy(model.state_dict())
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = ((model(MultiGraph([nf], [EdgeSet("mesh_edges", ef, s, r)])) - tgt) ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss
+
+        runner = step
+        if mode == "graph":
+            try:
+                runner = GraphedStep(step, params)
+            except RuntimeError as exc:                                           # e.g. an optimizer build that refuses capture
+                pytest.skip(f"whole-step capture not available here: {exc}")
+            model.load_state_dict(start)                                          # undo the warm-up / capture updates
+        losses = []
+        for b in batches:
+            for dst, src in zip((nf, ef, tgt), b):
+                dst.copy_(src)
+            losses.append(float(runner()))
+        results[mode] = (losses, [p.detach().clone() for p in params])
+    assert results["eager"][0] == results["graph"][0]
+    assert results["eager"][0][0] != results["eager"][0][2]
+    for a, b in zip(results["eager"][1], results["graph"][1]):
+        assert torch.equal(a, b)
