@@ -9,7 +9,7 @@
 // Bit-exact edge sets need the reference's distance arithmetic, not the textbook one.  torch.cdist (p = 2, more than 25 rows)
 // evaluates  d(i, j) = sqrt(max(0, x1_[i] . x2_[j]))  with  x1_[i] = [-2 x_i, |x_i|^2, 1],  x2_[j] = [x_j, 1, |x_j|^2]  as one
 // fp32 GEMM with K = 5: five fused multiply-adds in k order (checked against torch's CPU GEMM on 9 M pairs: 0 mismatches;
-// the direct form sqrt(sum (x_i - x_j)^2) differs from it in ~19 % of the entries).  |x|^2 = (x^2 + y^2) + z^2 with every
+// the direct form sqrt(sum (x_i - x_j)^2) differs from it in most entries (65 % of 640 000 pairs in the CPU test)).  |x|^2 = (x^2 + y^2) + z^2 with every
 // product and sum rounded (pow(2) and sum(-1) are separate ATen kernels).  we_distance() below is that arithmetic.
 //
 // Determinism: the only atomics are integer (cell counters, hash-table CAS, bounding box); the order in which receivers land
