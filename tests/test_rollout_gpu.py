@@ -94,9 +94,11 @@ def test_rollout_error_curve_vs_oracle():
 
 
 @pytest.mark.gpu
-def test_graphed_training_step_equals_eager_including_the_optimizer():
-    """fwd + bwd + SGD step captured in one CUDA graph (hgn_b200.graphed.GraphedStep) == the same three eager steps, bit for bit:
-    the kernels are deterministic and the weight-pack kernels are part of the graph, so replays see the updated weights."""
+def test_graphed_training_step_follows_eager_including_the_optimizer():
+    """fwd + bwd + SGD step captured in one CUDA graph (hgn_b200.graphed.GraphedStep) follows the same three eager steps: the
+    weight-pack kernels are part of the graph, so every replay sees the weights the previous replay's optimizer step wrote.  The
+    hgn_b200 kernels are deterministic; torch's own GEMMs (encoder / decoder) may pick another algorithm under capture, hence a
+    tolerance -- far below the distance to a run whose weights never change (what stale packed weights would reproduce)."""
     import copy
     from hgn_b200 import synthetic
     from hgn_b200.graphed import GraphedStep
@@ -106,9 +108,9 @@ def test_graphed_training_step_equals_eager_including_the_optimizer():
     s, r = (t.to(dev) for t in synthetic.grid_edges_two_way(20, 12))
     n, e = 240, s.numel()
     torch.manual_seed(1)
-    batches = [(torch.randn(n, 5, device=dev), torch.randn(e, 7, device=dev), torch.randn(n, 3, device=dev)) for _ in range(3)]
+    batches = [(torch.randn(n, 5, device=dev), torch.randn(e, 7, device=dev), torch.randn(n, 3, device=dev)) for _ in range(4)]
     results = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "frozen", "graph"):
         torch.manual_seed(0)
         model = MeshGraphNet(3, 128, 2, "sum", 3, "none", ["mesh_edges"]).to(dev)
         model.processor.precision = "bf16"
@@ -116,7 +118,7 @@ def test_graphed_training_step_equals_eager_including_the_optimizer():
         with torch.no_grad():
             model(MultiGraph([nf], [EdgeSet("mesh_edges", ef, s, r)]))            # materialise the lazy parameters
         params = list(model.parameters())
-        opt = torch.optim.SGD(params, lr=1e-2)
+        opt = torch.optim.SGD(params, lr=0.0 if mode == "frozen" else 0.05)
         start = copy.deepcopy(model.state_dict())
 
         def step():
@@ -132,14 +134,17 @@ def test_graphed_training_step_equals_eager_including_the_optimizer():
                 runner = GraphedStep(step, params)
             except RuntimeError as exc:                                           # e.g. an optimizer build that refuses capture
                 pytest.skip(f"whole-step capture not available here: {exc}")
-            model.load_state_dict(start)                                          # undo the warm-up / capture updates
+            model.load_state_dict(start)                                          # undo the warm-up updates
         losses = []
         for b in batches:
             for dst, src in zip((nf, ef, tgt), b):
                 dst.copy_(src)
             losses.append(float(runner()))
-        results[mode] = (losses, [p.detach().clone() for p in params])
-    assert results["eager"][0] == results["graph"][0]
-    assert results["eager"][0][0] != results["eager"][0][2]
-    for a, b in zip(results["eager"][1], results["graph"][1]):
-        assert torch.equal(a, b)
+        results[mode] = (losses, torch.cat([p.detach().reshape(-1) for p in params]).clone())
+    eager, frozen, graph = (results[k][0] for k in ("eager", "frozen", "graph"))
+    assert abs(graph[0] - eager[0]) <= 1e-3 * abs(eager[0])                       # same weights, same batch
+    for k in (1, 2, 3):
+        moved = abs(eager[k] - frozen[k])                                         # what the optimizer steps changed on this batch
+        assert abs(graph[k] - eager[k]) <= max(0.05 * moved, 1e-3 * abs(eager[k])), (k, graph[k], eager[k], frozen[k])
+    w_eager, w_frozen, w_graph = (results[k][1] for k in ("eager", "frozen", "graph"))
+    assert float((w_graph - w_eager).norm()) <= 0.05 * float((w_eager - w_frozen).norm())
