@@ -427,6 +427,37 @@ def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
         off += g.numel()
 
 
+_NORMALIZER_FIELDS = ("_acc_sum", "_acc_sum_squared", "_acc_count", "_num_accumulations")
+
+
+def allreduce_normalizers(normalizers, group=None) -> None:
+    """Keep the replicas' online feature statistics identical: every ``Normalizer``
+    (src/migration/normalizer.py:53-63) accumulates its own rank's batches; this sums, over the ranks, what each accumulated since
+    the previous call and adds it to the common state -- the totals a single process that had seen every rank's batches would hold
+    (``_num_accumulations`` advances by the world size per step, like that process's counter).  One flat all-reduce for all of them."""
+    normalizers = list(normalizers)
+    if not normalizers:
+        return
+    bases, deltas = [], []
+    for nz in normalizers:
+        base = getattr(nz, "_synced_state", None)
+        if base is None:
+            base = {f: torch.zeros_like(getattr(nz, f)) for f in _NORMALIZER_FIELDS}
+        bases.append(base)
+        deltas.extend((getattr(nz, f) - base[f]).reshape(-1).float() for f in _NORMALIZER_FIELDS)
+    flat = torch.cat(deltas)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for nz, base in zip(normalizers, bases):
+        state = {}
+        for f in _NORMALIZER_FIELDS:
+            cur = getattr(nz, f)
+            state[f] = base[f] + flat[off:off + cur.numel()].view_as(cur).to(cur.dtype)
+            off += cur.numel()
+            setattr(nz, f, state[f])
+        nz._synced_state = {f: t.clone() for f, t in state.items()}
+
+
 # ------------------------------------------------------------------------------------------------------
 # multi-GPU benchmark (bench.py --gpus N under torchrun)
 # ------------------------------------------------------------------------------------------------------

@@ -189,3 +189,53 @@ def test_two_rank_data_parallel_gradients_match_summed_batches(tmp_path):
     for g0, g1, ref in zip(per_rank[0], per_rank[1], weights.values()):
         assert torch.equal(g0, g1)                                   # replicas stay identical
         assert torch.allclose(g0, ref.grad, rtol=1e-5, atol=1e-6)
+
+
+def _norm_batch(step, rank):
+    g = torch.Generator().manual_seed(100 + 10 * step + rank)
+    return torch.randn(13 + rank, 5, generator=g) * (1.0 + rank) + step
+
+
+def _norm_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hgn_b200.migration.normalizer import Normalizer
+        nzs = [Normalizer(5, "a"), Normalizer(5, "b")]
+        outs = []
+        for step in range(3):
+            nzs[0](_norm_batch(step, rank), True)
+            if step != 1:
+                nzs[1](_norm_batch(step, rank) * 2.0, True)           # the second normaliser skips a step: zero increment there
+            partition.allreduce_normalizers(nzs)
+            outs.append(nzs[0](_norm_batch(7, 0), False))              # evaluation with the synchronised statistics
+        torch.save({"state": [[getattr(nz, f) for f in partition._NORMALIZER_FIELDS] for nz in nzs], "outs": outs},
+                   os.path.join(tmpdir, f"norm_rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_normalizer_statistics_match_one_process_seeing_all_batches(tmp_path):
+    """Replicas accumulate their own batches; `allreduce_normalizers` leaves every rank with the totals of a single process that
+    accumulated all ranks' batches (rank order within a step), so normalised features agree across replicas and with that process."""
+    from hgn_b200.migration.normalizer import Normalizer
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_norm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    ref = [Normalizer(5, "a"), Normalizer(5, "b")]
+    ref_outs = []
+    for step in range(3):
+        for rank in range(world):
+            ref[0](_norm_batch(step, rank), True)
+            if step != 1:
+                ref[1](_norm_batch(step, rank) * 2.0, True)
+        ref_outs.append(ref[0](_norm_batch(7, 0), False))
+    per_rank = [torch.load(os.path.join(tmp_path, f"norm_rank{k}.pt")) for k in range(world)]
+    for k in range(len(ref)):
+        for j, f in enumerate(partition._NORMALIZER_FIELDS):
+            a, b = per_rank[0]["state"][k][j], per_rank[1]["state"][k][j]
+            assert torch.equal(a, b), f                                            # replicas identical
+            assert torch.allclose(a, getattr(ref[k], f), rtol=1e-6, atol=1e-6), f
+    assert float(per_rank[0]["state"][0][3]) == 6.0 and float(per_rank[0]["state"][1][3]) == 4.0      # _num_accumulations
+    for o0, o1, r in zip(per_rank[0]["outs"], per_rank[1]["outs"], ref_outs):
+        assert torch.equal(o0, o1) and torch.allclose(o0, r, rtol=1e-4, atol=1e-5)
