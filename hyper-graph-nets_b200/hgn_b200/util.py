@@ -34,11 +34,30 @@ class NodeType(enum.IntEnum):  # src/util.py:27-35
     SIZE = 9
 
 
+_TOPOLOGY_CACHE = collections.OrderedDict()     # id(faces) -> (faces, version, deform, result); a handful of meshes at most
+
+
 def triangles_to_edges(faces: torch.Tensor, deform: bool = False):
     """Mesh edges from triangles (or, with ``deform``, tetrahedra: edges (0,1),(1,2),(2,3),(3,0) only).
 
     Bit-exact contract of src/util.py:50-89: unique undirected (max, min) pairs in lexicographic order
-    (``torch.unique(dim=0)``), int64, followed by the reversed copies in 'two_way_connectivity'."""
+    (``torch.unique(dim=0)``), int64, followed by the reversed copies in 'two_way_connectivity'.
+
+    The reference redoes the sort-based ``unique`` on every step of a rollout although the topology never changes along a
+    trajectory.  Calling this again with the SAME, unmodified tensor object returns the first result (the
+    cache holds the tensor, so its identity cannot be recycled; an in-place change bumps ``_version`` and misses)."""
+    hit = _TOPOLOGY_CACHE.get(id(faces))
+    if hit is not None and hit[0] is faces and hit[1] == faces._version and hit[2] == deform:
+        _TOPOLOGY_CACHE.move_to_end(id(faces))
+        return dict(hit[3])
+    result = _triangles_to_edges(faces, deform)
+    _TOPOLOGY_CACHE[id(faces)] = (faces, faces._version, deform, result)
+    while len(_TOPOLOGY_CACHE) > 8:
+        _TOPOLOGY_CACHE.popitem(last=False)
+    return dict(result)
+
+
+def _triangles_to_edges(faces: torch.Tensor, deform: bool):
     k = 4 if deform else 3
     pairs = torch.cat([torch.stack((faces[:, i], faces[:, (i + 1) % k]), dim=1) for i in range(k)], dim=0)
     receivers, _ = torch.min(pairs, dim=1)

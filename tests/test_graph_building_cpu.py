@@ -97,3 +97,25 @@ def test_get_batched_matches_live_reference_when_mounted():
             for e0, e1 in zip(g0.edge_sets, g1.edge_sets):
                 assert e0.name == e1.name and torch.equal(e0.senders, e1.senders) and torch.equal(e0.receivers, e1.receivers)
                 assert torch.equal(e0.features, e1.features)
+
+
+def test_triangles_to_edges_topology_cache():
+    from hgn_b200 import synthetic, util
+    import hgn_oracle as orc
+    cells = torch.from_numpy(synthetic.grid_triangles(7, 5)).long()
+    first = util.triangles_to_edges(cells)
+    again = util.triangles_to_edges(cells)
+    ref = orc.triangles_to_edges(cells)
+    for a, b, c in zip(first["two_way_connectivity"], again["two_way_connectivity"], ref["two_way_connectivity"]):
+        assert a is b and torch.equal(a, c)                      # same object from the cache, equal to the oracle
+    cells[0] = cells[0].flip(0)                                  # in-place change: the version check must miss
+    changed = util.triangles_to_edges(cells)
+    assert changed["senders"] is not first["senders"] and torch.equal(changed["senders"], orc.triangles_to_edges(cells)["senders"])
+    clone = cells.clone()                                        # another object with equal content: computed afresh, equal result
+    assert torch.equal(util.triangles_to_edges(clone)["receivers"], changed["receivers"])
+    tets = torch.from_numpy(synthetic.box_tetrahedra(3, 3, 2)).long()
+    d1, d2 = util.triangles_to_edges(tets, deform=True), orc.triangles_to_edges(tets, deform=True)
+    assert torch.equal(d1["senders"], d2["senders"]) and torch.equal(d1["receivers"], d2["receivers"])
+    for k in range(12):                                          # the cache stays small
+        util.triangles_to_edges(torch.from_numpy(synthetic.grid_triangles(3 + k, 3)).long())
+    assert len(util._TOPOLOGY_CACHE) <= 8
