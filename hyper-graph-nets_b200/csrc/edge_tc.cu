@@ -824,6 +824,10 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // 
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
                        const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name,
                        cudaStream_t st);                                                                                  // edge_fwd_tc.cu
+int edge_bwd_g4_launch(int64_t rows, int64_t tiles, int grid, const void* packed, const void* dense, const void* proj_s, const void* proj_r,
+                       const int32_t* senders, const int32_t* receivers, int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg,
+                       void* grad_dense, void* grad_pre0, float* w_partial, float* epi_colpart, float* prod_colpart, const char* name,
+                       cudaStream_t st);                         // edge_bwd_g4_tc.cu (experimental)
 int edge_bwd2_launch(int64_t rows, int64_t tiles, int grid, const void* packed, const void* dense, const void* proj_s, const void* proj_r,
                      const int32_t* senders, const int32_t* receivers, int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg,
                      void* grad_dense, void* grad_pre0, float* w_partial, float* epi_colpart, float* prod_colpart, const char* name,
@@ -895,6 +899,23 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
       edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi, prod, L.grid, w0_chunks, w0_chunk0, 1, gW0, gW1, gW2,
                                                                                 gb0, gb1, gb2, ggamma, gbeta);
       reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(pair, L.pair_parts, 2, 1, gW0, w0_chunks * kD, w0_chunk0 * kD);
+    }
+    HGN_LAUNCH_OK("edge_bwd_reduce");
+    return HGN_OK;
+  }
+  // HGN_EDGE_BWD_TMA_GATHER=1: the experimental variant whose table rows arrive by TMA gather4 (edge_bwd_g4_tc.cu; written after the
+  // round's GPU budget was spent -- compiled, not yet run).  Same partial buffers, same reduction.
+  const char* g4 = getenv("HGN_EDGE_BWD_TMA_GATHER");
+  if (g4 != nullptr && g4[0] == '1') {
+    float* w_partial = reinterpret_cast<float*>(ws + L.w_partial);
+    float* epi = reinterpret_cast<float*>(ws + L.epi);
+    float* prod = reinterpret_cast<float*>(ws + L.prod);
+    if (int rc = edge_bwd_g4_launch(rows, ceil_div(rows, kTile), L.grid, packed, dense, proj_s, proj_r, senders, receivers, w0_chunks, w0_chunk0,
+                                    grad_out, grad_agg, grad_dense, grad_pre0, w_partial, epi, prod, name, st)) return rc;
+    {
+      HGN_TIMED("reduce_weight_partials", st);
+      edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi, prod, L.grid, w0_chunks, w0_chunk0, 0, gW0, gW1, gW2,
+                                                                                gb0, gb1, gb2, ggamma, gbeta);
     }
     HGN_LAUNCH_OK("edge_bwd_reduce");
     return HGN_OK;

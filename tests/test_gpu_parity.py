@@ -5,6 +5,8 @@ live reference) and against the CPU oracle on seeded inputs.
 Tolerances (BASELINE.json north_star): fp32 mode 1e-5 relative, bf16 mode 2e-2 relative, with
 relative error = max|a-b| / max|b| per tensor; index structure bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -394,6 +396,50 @@ def test_interleaved_backward_kernel_matches_default(monkeypatch):
         runs[flag] = [v.grad, e.grad] + [p.grad for p in params]
     for a, b in zip(runs["0"], runs["1"]):
         assert rel_l2(a.float(), b.float()) < 2e-3
+
+
+@pytest.mark.skipif(not os.environ.get("HGN_TEST_EXPERIMENTAL"), reason="experimental kernel that has not run on a GPU yet: set HGN_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("with_pr,with_agg", [(True, True), (True, False), (False, False)])
+def test_tma_gather_backward_kernel_matches_default(with_pr, with_agg, monkeypatch):
+    """The experimental backward kernel whose table rows arrive by TMA gather4 (HGN_EDGE_BWD_TMA_GATHER=1, csrc/edge_bwd_g4_tc.cu)
+    against the default kernel: identical arithmetic on identical values, so the results must be bitwise equal.  (False, False) is the
+    node-update shape: identity gathers of one table, no aggregate gradient.  Not part of the default run until the kernel has been
+    brought up on a GPU (it was written after this round's GPU budget was spent)."""
+    monkeypatch.setattr(ops, "backward_mode", "recompute")
+    torch.manual_seed(6)
+    runs = {}
+    if with_pr:
+        w = _random_mlp_weights(3, 12)
+        n_nodes, rows = 3000, 70001
+        s = torch.randint(0, n_nodes, (rows,), device="cuda")
+        r = torch.randint(0, n_nodes, (rows,), device="cuda")
+        sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
+        v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+        e0 = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
+    else:
+        w = _random_mlp_weights(2, 13)
+        n_nodes = 40003
+        v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+        a0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("HGN_EDGE_BWD_TMA_GATHER", flag)
+        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
+        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
+        if with_pr:
+            v, e = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+            out, agg = ops.edge_update(params, {}, v, e, sp, rp, with_agg)
+            loss = out.float().sum() * 0.5 + (out.float() ** 2).sum()
+            if with_agg:
+                loss = loss + (agg.float() ** 2).sum()
+            loss.backward()
+            runs[flag] = [v.grad, e.grad] + [p.grad for p in params]
+        else:
+            v, ag = v0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+            out = ops.node_update(params, {}, v, [ag])
+            (out.float() ** 2).sum().backward()
+            runs[flag] = [v.grad, ag.grad] + [p.grad for p in params]
+    for a, b in zip(runs["0"], runs["1"]):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("mode", ["stash", "recompute"])
