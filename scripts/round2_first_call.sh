@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # First GPU call of the next round (everything here was prepared without a GPU):
 #   1. the gather-rate probe: TMA gather4 vs per-row ld.global, random and sorted indices, box {64,1} and {64,4}
+#   1b. the M = 64 accumulator layout / rate probe (two 64-row tiles in flight: DESIGN.md s8)
 #   2. the experimental TMA-gather backward kernel: bitwise parity against the default kernel, under a timeout (a hang must not cost the box)
 #   3. its timing against the default kernel on the cfg5 layer
 # usage: gpurun --timeout 900 -- scripts/round2_first_call.sh
@@ -8,6 +9,8 @@ mkdir -p gpurun_out
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o scripts/probes/gather_rate scripts/probes/gather_rate.cu -lcuda > gpurun_out/r2_probe_build.log 2>&1
 timeout 120 scripts/probes/gather_rate 1000000 5992002 0 > gpurun_out/r2_gather_random.log 2>&1; echo "probe random rc=$?"; tail -12 gpurun_out/r2_gather_random.log
 timeout 120 scripts/probes/gather_rate 1000000 5992002 1 > gpurun_out/r2_gather_sorted.log 2>&1; echo "probe sorted rc=$?"; tail -8 gpurun_out/r2_gather_sorted.log
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I hyper-graph-nets_b200/csrc -o scripts/probes/m64_layout scripts/probes/m64_layout.cu >> gpurun_out/r2_probe_build.log 2>&1
+timeout 60 scripts/probes/m64_layout > gpurun_out/r2_m64_layout.log 2>&1; echo "m64 layout rc=$?"; tail -14 gpurun_out/r2_m64_layout.log
 for box in 1 4; do
   HGN_GATHER4_BOX_ROWS=$box HGN_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k tma_gather > gpurun_out/r2_g4_pytest_box$box.log 2>&1
   echo "g4 parity (box rows $box) rc=$?"; tail -3 gpurun_out/r2_g4_pytest_box$box.log
