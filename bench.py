@@ -309,6 +309,157 @@ def run_ours(args):
         dist.barrier()
 
 
+# ------------------------------------------------------------------------------------------------------
+# --workload cfg3: HeteroGraphNet on a plateCluster-shaped batch (BASELINE.json configs[2], SURVEY.md s8 cfg 3).
+# WRITTEN AFTER THE ROUND'S GPU BUDGET WAS SPENT: not yet run on a GPU.  Not the driver's bench line.
+# ------------------------------------------------------------------------------------------------------
+CFG3_PLATE, CFG3_OBSTACLE, CFG3_BATCH, CFG3_LAYERS = (21, 20, 3), (4, 4, 4), 16, 5     # 1 260 plate + 64 obstacle nodes (plate.yaml: batch 16, 5 layers)
+CFG3_SETS = ["mesh_edges", "world_edges", "intra_cluster_to_mesh", "intra_cluster_to_cluster", "inter_cluster"]   # plate.py:49-57 + connector.initialize
+
+
+def plate_block_clusters(dims, block=(7, 2, 3)):
+    """Block clustering of the plate lattice (node id = (k * ny + j) * nx + i): the host-side stand-in for the reference's sklearn
+    clustering (out of scope).  Returns the clusters (index tensors) and the face-adjacent cluster pairs."""
+    nx, ny, nz = dims
+    bx, by, bz = (-(-nx // block[0]), -(-ny // block[1]), -(-nz // block[2]))
+    ids = torch.arange(nx * ny * nz).reshape(nz, ny, nx)
+    clusters, neighbors = [], []
+    for cz in range(bz):
+        for cy in range(by):
+            for cx in range(bx):
+                sub = ids[cz * block[2]:(cz + 1) * block[2], cy * block[1]:(cy + 1) * block[1], cx * block[0]:(cx + 1) * block[0]]
+                clusters.append(sub.reshape(-1).clone())
+                k = (cz * by + cy) * bx + cx
+                if cx + 1 < bx:
+                    neighbors.append(torch.tensor([k, k + 1]))
+                if cy + 1 < by:
+                    neighbors.append(torch.tensor([k, k + bx]))
+                if cz + 1 < bz:
+                    neighbors.append(torch.tensor([k, k + bx * by]))
+    return clusters, neighbors
+
+
+def build_plate_batch(dev, seed=0):
+    """One batched plateCluster-shaped latent graph: two-body plate frame -> tetra mesh edges, world edges (cell-list kernel),
+    hierarchical connector index lists over a block clustering of the plate body, 128-wide seeded latents, batch of 16 through the
+    reference's own batching rule (hgn_b200.batching.get_batched, hyper-index quirk included)."""
+    from hgn_b200 import synthetic
+    from hgn_b200 import util as hutil
+    from hgn_b200.batching import get_batched
+    from hgn_b200.rmp.hierarchical_connector import connector_indices
+    from hgn_b200.world_edges import world_edges
+    frame = synthetic.plate_frame(plate=CFG3_PLATE, obstacle=CFG3_OBSTACLE, seed=seed)
+    n = frame["world_pos"].shape[0]
+    ms, mr = hutil.triangles_to_edges(frame["cells"].long(), deform=True)["two_way_connectivity"]
+    ws, wr = world_edges(frame["world_pos"].to(dev), frame["node_type"].to(dev), ms.to(dev), mr.to(dev))
+    clusters, neighbors = plate_block_clusters(CFG3_PLATE)
+    idx = connector_indices(clusters, neighbors, n, False)
+    index_lists = {"mesh_edges": (ms, mr), "world_edges": (ws.cpu(), wr.cpu()), "intra_cluster_to_cluster": idx["intra_cluster_to_cluster"],
+                   "intra_cluster_to_mesh": idx["intra_cluster_to_mesh"], "inter_cluster": idx["inter_cluster"]}
+    gen = torch.Generator().manual_seed(seed)
+    data = []
+    for _ in range(CFG3_BATCH):
+        nodes = [torch.randn(n, LATENT, generator=gen), torch.randn(len(clusters), LATENT, generator=gen)]
+        sets = [hutil.EdgeSet(name, torch.randn(s_.numel(), LATENT, generator=gen), s_, r_) for name, (s_, r_) in index_lists.items()]
+        data.append((hutil.MultiGraph(nodes, sets), {}))
+    (graph, _), = get_batched(data, CFG3_BATCH)
+    return graph, {"nodes": n * CFG3_BATCH, "hyper_nodes": len(clusters) * CFG3_BATCH,
+                   "edges": {es.name: int(es.senders.numel()) for es in graph.edge_sets}}
+
+
+def run_cfg3(args):
+    """HeteroGraphNet processor (pna, 5 layers, 5 edge sets, mesh + hyper nodes) fwd+bwd on the batched plate graph: edge-updates/s
+    over ALL edge sets, the per-kernel table, the CPU oracle and the torch-CUDA reference beside it."""
+    from hgn_b200 import _cabi, ops
+    from hgn_b200.migration.meshgraphnet import MeshGraphNet
+    from hgn_b200.util import MultiGraph
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    graph_host, sizes = build_plate_batch(dev)
+    e_total = sum(sizes["edges"].values())
+    torch.manual_seed(0)
+    proc = MeshGraphNet(3, LATENT, 2, "pna", CFG3_LAYERS, "hetero", CFG3_SETS).processor.to(dev)
+    proc.precision = "bf16"
+    nodes_dev = [t.to(dev) for t in graph_host.node_features]
+    sets_dev = [es._replace(features=es.features.to(dev), senders=es.senders.to(dev), receivers=es.receivers.to(dev)) for es in graph_host.edge_sets]
+    coef = torch.randn(nodes_dev[0].shape, generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def step():
+        for p in proc.parameters():
+            p.grad = None
+        nodes = [t.detach().requires_grad_(True) for t in nodes_dev]
+        sets = [es._replace(features=es.features.detach().requires_grad_(True)) for es in sets_dev]
+        out = proc(MultiGraph(nodes, sets))
+        loss = (out.node_features[0] * coef).sum() + sum(es.features.float().sum() for es in out.edge_sets) * 1e-3
+        loss.backward()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    _cabi.profile(True)
+    launches0 = ops.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            step()
+        stop.record()
+        torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / args.steps
+    launches = ops.launch_count - launches0
+    kernels = _cabi.profile_report()
+    _cabi.profile(False)
+    d2 = LATENT * LATENT
+    k_aggr = 4 * len(CFG3_SETS)
+    flops = 3 * (e_total * F_EDGE + (sizes["nodes"] + sizes["hyper_nodes"]) * 2 * ((1 + k_aggr) + 2) * d2) * CFG3_LAYERS   # SURVEY.md s8d
+    peak = load_peaks()["bf16_tflops_sustained"]
+    graphed = graphed_step(step, list(proc.parameters()), args.steps, e_total * CFG3_LAYERS)
+    # baselines: the oracle port on the host cores and on the GPU through torch's own kernels (same weights, same graph)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgn_oracle as orc
+    weights = {"processor." + k: v.detach().float() for k, v in proc.state_dict().items()}
+
+    def oracle_pass(device):
+        w = {k: v.to(device).requires_grad_(True) for k, v in weights.items()}
+        nodes = [t.to(device).clone().requires_grad_(True) for t in graph_host.node_features]
+        sets = [orc.EdgeSet(es.name, es.features.to(device).clone().requires_grad_(True), es.senders.to(device), es.receivers.to(device))
+                for es in graph_host.edge_sets]
+        out = orc.processor(w, "pna", "hetero", orc.MultiGraph(nodes, sets))
+        ((out.node_features[0] * coef.to(device)).sum() + sum(es.features.sum() for es in out.edge_sets) * 1e-3).backward()
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    oracle_pass("cpu")                              # one pass (~15-20 s: the pna aggregates of five edge sets); no separate warm-up
+    cpu_s = time.perf_counter() - t0
+    oracle_pass(dev); oracle_pass(dev)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        oracle_pass(dev)
+    b.record()
+    torch.cuda.synchronize()
+    ref_ms = a.elapsed_time(b) / 3
+    print(json.dumps({
+        "metric": METRIC, "value": e_total * CFG3_LAYERS / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (seeded two-body plate lattice, block clustering, seeded latents and weights)",
+        "config": {"workload": f"cfg3: plateCluster-shaped deforming plate ({sizes['nodes'] // CFG3_BATCH} nodes x batch {CFG3_BATCH}), HeteroGraphNet, "
+                               f"{CFG3_LAYERS} layers, pna, edge sets {sizes['edges']}, {sizes['hyper_nodes']} hyper nodes, processor fwd+bwd",
+                   "l2_policy": "small mesh: the step's working set is L2-resident by construction (launch-bound shape)"},
+        "gpu_launches": launches, "clocks": clocks.summary(),
+        "layer_roofline": {"tensor_ms_per_layer": flops / CFG3_LAYERS / (peak * 1e12) * 1e3, "measured_ms_per_layer": ms / CFG3_LAYERS,
+                           "frac": flops / (peak * 1e12) * 1e3 / ms},
+        "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
+        "cuda_graph": graphed,
+        "cpu_baseline": {"value": e_total * CFG3_LAYERS / cpu_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "seconds_per_pass": cpu_s,
+                         "sample": "the same batched graph and weights, fwd+bwd, fp32, oracle/hgn_oracle.py (block_hetero)"},
+        "torch_cuda_reference": {"value": e_total * CFG3_LAYERS / (ref_ms * 1e-3), "unit": UNIT, "ms_per_pass": ref_ms, "kind": "port on torch CUDA ops"},
+    }))
+
+
 def graphed_step(step_fn, params, steps, edge_updates_per_step):
     """The resident step replayed as one CUDA graph (the small-mesh shapes are launch-bound: ~1 100 launches of a few
     microseconds each per step).  Whole-step capture in the usual PyTorch way: warm up on a side stream, drop the gradients so that
@@ -593,11 +744,14 @@ def main():
     ap.add_argument("--aggregator", default=None, choices=["sum", "pna"],
                     help="message-passing aggregator (default: the workload's; the headline metric is quoted on 'sum'; 'pna' is the "
                          "reference configs' default)")
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS),
-                    help="cfg5 = the headline 1M/6M mesh (the bench line); cfg2 / cfg4 = small-mesh batched training shapes")
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + ["cfg3"],
+                    help="cfg5 = the headline 1M/6M mesh (the bench line); cfg2 / cfg4 = small-mesh batched training shapes; "
+                         "cfg3 = HeteroGraphNet on a plateCluster-shaped batch (single GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg3":
+        run_cfg3(args)
     else:
         run_ours(args)
 

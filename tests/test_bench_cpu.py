@@ -55,3 +55,25 @@ def test_batched_workload_is_disjoint_copies_of_the_mesh():
         assert torch.equal(three["senders"][i * e:(i + 1) * e], one["senders"] + i * n)
         assert torch.equal(three["receivers"][i * e:(i + 1) * e], one["receivers"] + i * n)
     assert set(bench.WORKLOADS) == {"cfg2", "cfg4", "cfg5"} and bench.WORKLOADS["cfg5"][:5] == (1000, 1000, 1, 15, "sum")
+
+
+def test_cfg3_plate_clustering_and_batched_graph(monkeypatch):
+    # block clustering: a disjoint cover of the plate body, 30 clusters (plateCluster.yaml asks for 31), face-adjacent neighbour pairs
+    clusters, neighbors = bench.plate_block_clusters(bench.CFG3_PLATE)
+    n_plate = bench.CFG3_PLATE[0] * bench.CFG3_PLATE[1] * bench.CFG3_PLATE[2]
+    members = torch.cat(clusters)
+    assert len(clusters) == 30 and members.numel() == n_plate and torch.equal(members.sort().values, torch.arange(n_plate))
+    assert all(0 <= int(p[0]) < int(p[1]) < len(clusters) for p in neighbors) and len({tuple(p.tolist()) for p in neighbors}) == len(neighbors)
+    # the batched graph, with the world-edge kernel replaced by the dense oracle (no GPU here)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import hgn_oracle as orc
+    import hgn_b200.world_edges as we
+    monkeypatch.setattr(we, "world_edges", lambda pos, types, ms, mr, **kw: orc.world_edges(pos.cpu(), types.cpu(), ms.cpu(), mr.cpu()))
+    graph, sizes = bench.build_plate_batch(torch.device("cpu"))
+    n = (n_plate + 64) * bench.CFG3_BATCH
+    assert sizes["nodes"] == n and sizes["hyper_nodes"] == 30 * bench.CFG3_BATCH and sizes["edges"]["world_edges"] > 0
+    assert [es.name for es in graph.edge_sets] == ["mesh_edges", "world_edges", "intra_cluster_to_cluster", "intra_cluster_to_mesh", "inter_cluster"]
+    assert set(bench.CFG3_SETS) == {es.name for es in graph.edge_sets}
+    for es in graph.edge_sets:
+        assert es.features.shape == (es.senders.numel(), 128) and int(es.senders.min()) >= 0
+        assert int(max(es.senders.max(), es.receivers.max())) < n + sizes["hyper_nodes"]
