@@ -18,3 +18,4 @@ done
 timeout 120 python scripts/time_edge.py 2> /dev/null | tail -1
 HGN_EDGE_BWD_TMA_GATHER=1 timeout 120 python scripts/time_edge.py 2> gpurun_out/r2_g4_time.err | tail -1
 HGN_EDGE_BWD_TMA_GATHER=1 HGN_TC_ABLATE=64 timeout 120 python scripts/time_edge.py 2> gpurun_out/r2_g4_timeline.log | tail -1
+HGN_BENCH_NO_TORCH_REFERENCE=1 timeout 400 python bench.py --workload cfg3 --steps 5 > gpurun_out/r2_cfg3.json 2> gpurun_out/r2_cfg3.err; echo "cfg3 rc=$?"; tail -c 600 gpurun_out/r2_cfg3.json; tail -3 gpurun_out/r2_cfg3.err
