@@ -610,7 +610,8 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // 
 
 // 2-D map over a [rows][128] bf16 table for tile::gather4: 64-column (128-byte) boxes, 128B swizzle.  The table's row count is not
 // known to the launcher (the C ABI passes only the edge count), so the map spans 2^30 rows: the indices are the plan's, in range.
-// Box height: HGN_GATHER4_BOX_ROWS (default 1; scripts/probes/gather_rate.cu settles which the instruction wants).
+// Box height 1 (CuTe builds its gather4 descriptors the same way: make_tma_copy_atom composes the box to {columns, 1} and counts four
+// boxes per instruction); HGN_GATHER4_BOX_ROWS overrides it for the bring-up probe.
 typedef CUresult (*EncodeTiledFnG4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static int make_gather_tensor_map(CUtensorMap* tm, const void* base) {

@@ -7,7 +7,7 @@
 // and checks both against a host checksum.  Build and run (one GPU):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o scripts/probes/gather_rate scripts/probes/gather_rate.cu -lcuda
 //   scripts/probes/gather_rate [rows_in_table=1000000] [gathers=5992002] [sorted=0|1]
-// Open questions it answers: the box shape tile::gather4 wants ({64, 1} is tried first, then {64, 4}), bytes/cycle/SM of both
+// Open questions it answers: the box shape tile::gather4 wants ({64, 1} -- what CuTe's make_tma_copy_atom encodes -- then {64, 4}), bytes/cycle/SM of both
 // modes for random and for receiver-sorted indices, and whether one issuing thread keeps up.
 #include <cuda.h>
 #include <cuda_bf16.h>
