@@ -60,7 +60,7 @@ gather_kernel(int mode, const __nv_bfloat16* __restrict__ table, const int32_t* 
         if (g < gathers) {
           const uint4* src = reinterpret_cast<const uint4*>(table + int64_t(__ldg(idx + g)) * kD + hh * 64);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { const uint4 v = __ldg(src + k); sum += v.x + v.y + v.z + v.w; }
+          for (int k = 0; k < 8; ++k) { const uint4 v = __ldg(src + k); sum += (unsigned long long)v.x + v.y + v.z + v.w; }
         }
       }
     }
@@ -91,7 +91,7 @@ gather_kernel(int mode, const __nv_bfloat16* __restrict__ table, const int32_t* 
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint4 v = *reinterpret_cast<const uint4*>(base + sw128(r, k));
-          if (g < gathers) sum += v.x + v.y + v.z + v.w;
+          if (g < gathers) sum += (unsigned long long)v.x + v.y + v.z + v.w;
         }
         mbar_arrive(&empty[s]);
       }
