@@ -58,9 +58,15 @@ gather_kernel(int mode, const __nv_bfloat16* __restrict__ table, const int32_t* 
       for (int64_t t = 0; t < my_tiles; ++t) {
         const int64_t g = (blockIdx.x + t * gridDim.x) * kTile + r;
         if (g < gathers) {
-          const uint4* src = reinterpret_cast<const uint4*>(table + int64_t(__ldg(idx + g)) * kD + hh * 64);
+          const __nv_bfloat16* src = table + int64_t(__ldg(idx + g)) * kD + hh * 64;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { const uint4 v = __ldg(src + k); sum += (unsigned long long)v.x + v.y + v.z + v.w; }
+          for (int k = 0; k < 4; ++k) {                       // the kernel's ldg256_l1: one 32-byte sector per lane and instruction
+            uint32_t v[8];
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(src + 16 * k));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[j];
+          }
         }
       }
     }
