@@ -40,6 +40,8 @@ def test_size_queries_need_no_gpu():
     assert lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_BF16, 1000) > 3 * 128 * 128 * 4
     assert lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, 1000) > 1000 * 128 * 2
     assert lib.hgn_edge_update_backward_workspace_bytes(_cabi.HGN_F32, 1000) == 0      # bf16-only entry points say so
+    small, big = lib.hgn_world_edges_workspace_bytes(1000, 6000), lib.hgn_world_edges_workspace_bytes(1000000, 6000000)
+    assert 0 < small < big and big < 400 * 2 ** 20 and lib.hgn_world_edges_workspace_bytes(0, 0) > 0      # O(N): ~150 MiB at 1 M nodes, not N^2
 
 
 @pytest.mark.parametrize("name", MODEL_CASES)
