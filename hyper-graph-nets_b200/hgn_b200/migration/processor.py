@@ -45,7 +45,21 @@ class Processor(nn.Module):
             nodes[i] = nodes[i].to(torch.bfloat16)
         graph = latent_graph._replace(edge_sets=[es._replace(features=es.features.to(torch.bfloat16))
                                                  for es in latent_graph.edge_sets])
+        orders = None
+        if config.edge_storage() == 'receiver_sorted':       # experimental: see plan.EdgeStorageOrder
+            from ..plan import edge_storage_order, to_device_index
+            dev = graph.node_features[0].device
+            orders = {}
+            sets = []
+            for es in graph.edge_sets:
+                order = edge_storage_order(to_device_index(es.senders, dev), to_device_index(es.receivers, dev))
+                orders[es.name] = (order, es.senders, es.receivers)
+                sets.append(es._replace(features=order.store(es.features), senders=order.senders, receivers=order.receivers))
+            graph = graph._replace(edge_sets=sets)
         graph = self.graphnet_blocks(graph)
+        if orders is not None:                                # rows, and the caller's own index tensors, back in the reference order
+            graph = graph._replace(edge_sets=[es._replace(features=orders[es.name][0].restore(es.features), senders=orders[es.name][1],
+                                                          receivers=orders[es.name][2]) for es in graph.edge_sets])
         for i in range(len(graph.node_features)):
             graph.node_features[i] = graph.node_features[i].to(in_dtype)
         if not getattr(self, 'restore_edge_dtype', False):

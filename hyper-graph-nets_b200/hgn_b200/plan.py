@@ -103,5 +103,49 @@ def to_device_index(ids: torch.Tensor, device: torch.device) -> torch.Tensor:
     return dev_ids
 
 
+class EdgeStorageOrder:
+    """Receiver-sorted STORAGE order of one edge set (experimental, ``HGN_EDGE_STORAGE=receiver_sorted``; DESIGN.md s8 round-2 plan).
+
+    The reference's edge order (util.py:60-69: unique (max, min) pairs, then the reversed copies) is half sender-sorted and half
+    receiver-sorted.  Keeping the rows stably sorted by receiver INSIDE the processor makes every receiver's edges contiguous: the
+    ``Pr[r]`` / ``grad_agg[r]`` row gathers of the edge kernels then touch ~6 distinct rows per warp instruction instead of ~17
+    (scripts/analysis_gather_locality.py), and the aggregation becomes a reduction over consecutive rows (the precondition for
+    fusing it into the edge kernels' epilogues).  The sort is stable, so within a segment the rows keep their ascending reference
+    order: the receiver-side CSR kernels sum them in the same order, so the forward results are bitwise those of the reference
+    order (the sender-side sums of the backward see another order: gradients agree to fp32 / bf16 rounding).
+
+    ``perm[k]`` = reference id of the k-th stored row; ``inverse[i]`` = storage position of reference row i.  One instance per
+    receivers tensor (cached like the segment plans); ``senders`` / ``receivers`` are the permuted int64 index tensors, created once so
+    that their own segment plans stay cached across steps."""
+
+    def __init__(self, senders: torch.Tensor, receivers: torch.Tensor):
+        self.perm = torch.argsort(receivers, stable=True)
+        self.inverse = torch.empty_like(self.perm)
+        self.inverse[self.perm] = torch.arange(self.perm.numel(), device=self.perm.device, dtype=self.perm.dtype)
+        self.senders = senders.index_select(0, self.perm).contiguous()
+        self.receivers = receivers.index_select(0, self.perm).contiguous()
+        self.version = (senders._version, receivers._version)
+
+    def store(self, features: torch.Tensor) -> torch.Tensor:
+        """Rows in storage order (differentiable: the backward scatters every gradient row to exactly one place)."""
+        return features.index_select(0, self.perm)
+
+    def restore(self, features: torch.Tensor) -> torch.Tensor:
+        """Rows back in the reference order."""
+        return features.index_select(0, self.inverse)
+
+
+def edge_storage_order(senders: torch.Tensor, receivers: torch.Tensor) -> EdgeStorageOrder:
+    """Cached per (senders, receivers) tensor pair, like ``segment_plan``."""
+    key = ("order", senders.data_ptr(), receivers.data_ptr(), receivers.numel(), str(receivers.device))
+    hit = _plans.get(key)
+    if hit is not None and hit[2].version == (senders._version, receivers._version):
+        _plans.move_to_end(key)
+        return hit[2]
+    order = EdgeStorageOrder(senders, receivers)
+    _remember(key, (senders, receivers, order))
+    return order
+
+
 def clear_plan_cache() -> None:
     _plans.clear()

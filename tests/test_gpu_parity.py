@@ -442,6 +442,37 @@ def test_tma_gather_backward_kernel_matches_default(with_pr, with_agg, monkeypat
         assert torch.equal(a, b)
 
 
+@pytest.mark.skipif(not os.environ.get("HGN_TEST_EXPERIMENTAL"), reason="experimental path that has not run on a GPU yet: set HGN_TEST_EXPERIMENTAL=1")
+def test_receiver_sorted_edge_storage_is_transparent():
+    """HGN_EDGE_STORAGE=receiver_sorted (plan.EdgeStorageOrder): the bf16 processor keeps its edge rows sorted by receiver between
+    entry and exit.  Forward results are bitwise those of the reference order (stable sort: every receiver's rows keep their order);
+    gradients agree to rounding (the sender-side sums see another order)."""
+    from hgn_b200 import config
+    s, r = (t.cuda() for t in synthetic.grid_edges_two_way(40, 30))
+    n, e = 1200, s.numel()
+    w = synthetic.seeded_state_dict(synthetic.processor_shapes(3, ["mesh_edges"], "sum"), 21)
+    v0 = synthetic.seeded_tensor("rs_v", (n, 128), 2).cuda()
+    e0 = synthetic.seeded_tensor("rs_e", (e, 128), 2).cuda()
+    runs = {}
+    try:
+        for mode in ("reference", "receiver_sorted"):
+            config.set_edge_storage(mode)
+            proc = MeshGraphNet(3, 128, 2, "sum", 3, "none", ["mesh_edges"]).processor
+            proc.load_state_dict({k[len("processor."):]: t for k, t in w.items()})
+            proc = proc.cuda()
+            proc.precision = "bf16"
+            v, ed = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+            out = proc(hutil.MultiGraph([v], [hutil.EdgeSet("mesh_edges", ed, s, r)]))
+            assert out.edge_sets[0].senders is s and out.edge_sets[0].receivers is r
+            ((out.node_features[0] ** 2).sum() + out.edge_sets[0].features.float().sum()).backward()
+            runs[mode] = (out.node_features[0].detach(), out.edge_sets[0].features.detach(), v.grad, ed.grad)
+    finally:
+        config.set_edge_storage("reference")
+    a, b = runs["reference"], runs["receiver_sorted"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert rel_l2(b[2].float(), a[2].float()) < 2e-2 and rel_l2(b[3].float(), a[3].float()) < 2e-2
+
+
 @pytest.mark.parametrize("mode", ["stash", "recompute"])
 def test_projected_edge_update_is_deterministic(mode, monkeypatch):
     monkeypatch.setattr(ops, "backward_mode", mode)

@@ -119,3 +119,32 @@ def test_triangles_to_edges_topology_cache():
     for k in range(12):                                          # the cache stays small
         util.triangles_to_edges(torch.from_numpy(synthetic.grid_triangles(3 + k, 3)).long())
     assert len(util._TOPOLOGY_CACHE) <= 8
+
+
+def test_receiver_sorted_edge_storage_is_a_stable_permutation_and_transparent():
+    """plan.EdgeStorageOrder (experimental HGN_EDGE_STORAGE=receiver_sorted): stable sort by receiver, exact inverse, and the
+    processor result is the same function of the graph -- checked with the CPU oracle on the permuted and on the original edge set."""
+    import hgn_oracle as orc
+    from hgn_b200 import synthetic
+    from hgn_b200.plan import EdgeStorageOrder
+    s, r = synthetic.grid_edges_two_way(9, 7)
+    order = EdgeStorageOrder(s, r)
+    e = s.numel()
+    assert torch.equal(order.perm.sort().values, torch.arange(e)) and torch.equal(order.perm[order.inverse], torch.arange(e))
+    assert bool((order.receivers[1:] >= order.receivers[:-1]).all())                                   # sorted by receiver
+    same = order.receivers[1:] == order.receivers[:-1]
+    assert bool((order.perm[1:][same] > order.perm[:-1][same]).all())                                  # stable inside a receiver
+    assert torch.equal(order.senders, s[order.perm]) and torch.equal(order.receivers, r[order.perm])
+    feats = synthetic.seeded_tensor("so_e", (e, 128), 4)
+    assert torch.equal(order.restore(order.store(feats)), feats)
+    w = synthetic.seeded_state_dict(synthetic.processor_shapes(2, ["mesh_edges"], "sum"), 9)
+    v = synthetic.seeded_tensor("so_v", (63, 128), 4)
+    ref = orc.processor(w, "sum", "none", orc.MultiGraph([v.clone()], [orc.EdgeSet("mesh_edges", feats, s, r)]))
+    out = orc.processor(w, "sum", "none", orc.MultiGraph([v.clone()], [orc.EdgeSet("mesh_edges", order.store(feats), order.senders, order.receivers)]))
+    assert torch.allclose(out.node_features[0], ref.node_features[0], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(order.restore(out.edge_sets[0].features), ref.edge_sets[0].features, rtol=1e-5, atol=1e-5)
+    # distinct rows per 32 consecutive stored edges: the point of the exercise
+    def distinct(x):
+        x = x[: (x.numel() // 32) * 32].reshape(-1, 32).sort(dim=1).values
+        return float((1 + (x[:, 1:] != x[:, :-1]).sum(1)).float().mean())
+    assert distinct(order.receivers) < 0.6 * distinct(r)
