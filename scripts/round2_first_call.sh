@@ -22,3 +22,4 @@ HGN_BENCH_NO_TORCH_REFERENCE=1 timeout 400 python bench.py --workload cfg3 --ste
 HGN_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k receiver_sorted > gpurun_out/r2_sorted_pytest.log 2>&1; echo "sorted storage parity rc=$?"; tail -3 gpurun_out/r2_sorted_pytest.log
 HGN_EDGE_STORAGE=receiver_sorted HGN_BENCH_NO_ROLLOUT=1 HGN_BENCH_NO_TORCH_REFERENCE=1 timeout 400 python bench.py --steps 3 > gpurun_out/r2_sorted_bench.json 2> gpurun_out/r2_sorted_bench.err; echo "sorted storage bench rc=$?"
 python -c "import json;d=json.loads(open('gpurun_out/r2_sorted_bench.json').read().strip().splitlines()[-1]);print('receiver-sorted storage:',round(d['value']/1e6,1),'M/s',{k['name']:round(k['ms_per_step'],2) for k in d['kernels']})"
+HGN_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_rollout_gpu.py -x -q -m gpu -k graphed > gpurun_out/r2_graphed_pytest.log 2>&1; echo "graphed training step rc=$?"; tail -3 gpurun_out/r2_graphed_pytest.log
