@@ -31,6 +31,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "hyper-graph-nets_b200"))
 
+# The reference arm runs the UNMODIFIED reference on the host cores.  Its modules capture `src.util.device` at import time
+# (src/util.py:9: cuda when available), so that arm must not see a GPU: hide them before torch is imported.
+_REFERENCE_ARM = any(a == "reference" and i > 0 and sys.argv[i - 1] == "--impl" for i, a in enumerate(sys.argv)) or "--impl=reference" in sys.argv
+if _REFERENCE_ARM:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    os.environ.setdefault("WANDB_MODE", "disabled")
+
 import torch  # noqa: E402
 
 GRID_W, GRID_H = 1000, 1000
@@ -268,7 +275,7 @@ def run_ours(args):
     roofline = dominant_kernel_roofline(kernels, args.steps, e, n, peaks)
 
     # ---- CPU baseline: oracle port on a bounded sub-mesh ------------------------------------------------
-    cpu = cpu_baseline(steps=1, sample=cpu_sample, aggregator=args.aggregator) if world == 1 else None
+    cpu = cpu_baseline(steps=1, sample=cpu_sample, aggregator=args.aggregator, workload=args.workload) if world == 1 else None
     if rank != 0:
         dist.barrier()
         return
@@ -281,7 +288,7 @@ def run_ours(args):
                                "processor fwd+bwd", "nodes": n, "edges": e, "layers": layers, "latent": LATENT,
                    "l2_policy": ("inputs larger than L2 (1.8 GB of bf16 latents per layer)" if args.workload == "cfg5" else
                                  "small mesh: the whole step's working set is L2-resident by construction (launch-bound shape)"),
-                   "partitioning": "none", "backward": ops.backward_mode,
+                   "partitioning": "none", "backward": "recompute",
                    "parallelism": (f"dp{world}: one replica and one batch (seed = rank) per GPU, one flat fp32 gradient all-reduce (NCCL) per "
                                    "step; value = all ranks' edge updates / max-over-ranks time") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
@@ -505,8 +512,7 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
     # name -> (rows per launch, algorithmic flops per row, executed flops per row)
     tensor = {
         "edge_fwd_tc": (e, F_EDGE, 6 * d2), "edge_bwd_tc": (e, 2 * F_EDGE, 18 * d2),
-        "edge_bwd_stash_tc": (e, 2 * F_EDGE, 14 * d2),
-        "node_fwd_tc": (n, F_NODE_SUM, 6 * d2), "node_bwd_tc": (n, 2 * F_NODE_SUM, 18 * d2), "node_bwd_stash_tc": (n, 2 * F_NODE_SUM, 14 * d2),
+        "node_fwd_tc": (n, F_NODE_SUM, 6 * d2), "node_bwd_tc": (n, 2 * F_NODE_SUM, 18 * d2),
         "mlp_tile_tc_fwd": (n, F_NODE_SUM, F_NODE_SUM), "mlp_tile_tc_bwd": (n, F_NODE_SUM, 2 * F_NODE_SUM),
         "mlp_wgrad_tc": (n, F_NODE_SUM, F_NODE_SUM),
     }.get(top["name"])
@@ -549,83 +555,89 @@ def _cloth_features(world, prev, mesh_pos, pinned_type, senders, receivers):
     return node_features, edge_features
 
 
-def rollout_bench(dev):
-    """Closed-loop rollout (flag.py:194-246: predict, second-order integrate, pin the handle nodes, rebuild the graph) of the whole
-    encode-process-decode model in bf16 processor mode, eager and as one CUDA graph per step.  Returns the JSON sub-object."""
+def flag_model_params(aggregation="pna", steps=LAYERS):
+    """The model section of configs/flag.yaml without remote message passing (BASELINE.json configs[1]: MeshGraphNets, 15 MP layers)."""
+    return {"size": 3, "aggregation": aggregation, "message_passing_steps": steps,
+            "rmp": {"num_clusters": 10, "hyper_noise": "none", "hyper_node_features": True, "frequency": 1, "clustering": "none",
+                    "connector": "none", "fully_connect": False,
+                    "intra_cluster_sampling": {"enabled": False, "alpha": 0.1, "spotter_threshold": 0},
+                    "hdbscan": {"max_cluster_size": 50, "min_cluster_size": 20, "min_samples": 1, "spotter_threshold": 0.9}},
+            "graph_balancer": {"algorithm": "none", "frequency": 1, "remove_edges": True, "ricci": {"loops": 150, "tau": 150},
+                               "random": {"edge_amount": 100}}}
+
+
+def rollout_model_and_trajectory(FlagModel, dev, steps):
+    """The reference's own ``FlagModel`` (src/model/flag.py; on whatever ``src.migration`` modules are installed in this process) with
+    seeded weights and normaliser statistics, and a synthetic ``[T, N, .]`` trajectory dict for ``model.rollout``."""
     from hgn_b200 import synthetic
-    from hgn_b200 import util as hutil
-    from hgn_b200.migration.meshgraphnet import MeshGraphNet
-    frame = synthetic.cloth_frame(ROLLOUT_W, ROLLOUT_H, seed=1)
-    edges = hutil.triangles_to_edges(frame["cells"].long())
-    senders, receivers = (t.to(dev) for t in edges["two_way_connectivity"])
-    mesh_pos = frame["mesh_pos"].to(dev)
-    node_type = frame["node_type"].to(dev)
-    pinned = torch.ne(node_type[:, 0], 0).unsqueeze(-1)
-    pinned_type = torch.nn.functional.one_hot(pinned[:, 0].long(), 2).float()
     torch.manual_seed(0)
-    model = MeshGraphNet(3, LATENT, 2, "sum", LAYERS, "none", ["mesh_edges"]).to(dev)
-    model.processor.precision = "bf16"
-    world = frame["world_pos"].to(dev).clone()
-    prev = frame["prev|world_pos"].to(dev).clone()
-    world0, prev0 = world.clone(), prev.clone()
-
-    def one_step():
-        nf, ef = _cloth_features(world, prev, mesh_pos, pinned_type, senders, receivers)
-        acc = model(hutil.MultiGraph([nf], [hutil.EdgeSet("mesh_edges", ef, senders, receivers)]))
-        nxt = torch.where(pinned, world, 2 * world - prev + 0.01 * acc)
-        prev.copy_(world)
-        world.copy_(nxt)
-
-    def timed(fn, steps):
-        world.copy_(world0); prev.copy_(prev0)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return steps / (a.elapsed_time(b) * 1e-3)
-
-    out = {"config": f"{ROLLOUT_W}x{ROLLOUT_H} flag-style cloth ({world.shape[0]} nodes, {senders.numel()} directed edges), encoder + {LAYERS} GraphNet "
-                     f"layers (sum, bf16 processor) + decoder, {ROLLOUT_STEPS} closed-loop steps, graph features rebuilt on the device every step",
-           "unit": "rollout steps/s"}
+    model = FlagModel(flag_model_params())
+    base = synthetic.cloth_frame(ROLLOUT_W, ROLLOUT_H, seed=1)
+    n = ROLLOUT_W * ROLLOUT_H
+    drift = synthetic.seeded_tensor("rollout_drift", (n, 3), 2)
+    pos = [base["world_pos"] + 0.002 * t * drift for t in range(-1, 4)]
+    frames = [{**base, "prev|world_pos": pos[t], "world_pos": pos[t + 1], "target|world_pos": pos[t + 2]} for t in range(3)]
+    frames = [{k: v.to(dev) for k, v in f.items()} for f in frames]
+    model.train()
+    for f in frames:                                     # normaliser statistics (flag.py:96, 115, 192)
+        g = model.build_graph(f, True)
+        model.get_target(f, True)
     with torch.no_grad():
-        for _ in range(5):
-            one_step()                                   # lazy linears, plans, packed weights
-        out["eager"] = timed(one_step, ROLLOUT_STEPS)
-        eager_final = world.clone()
+        model(g)
+    net = model.learned_model
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict({k: v.to(dev) for k, v in synthetic.seeded_state_dict(shapes, 29).items()})
+    model.eval()
+    traj = {k: v.unsqueeze(0).expand(steps, *v.shape).contiguous() for k, v in frames[0].items()}
+    return model, traj
+
+
+def rollout_bench(dev):
+    """The metric's second half (BASELINE.json configs[1]): 400 closed-loop steps of a flag_simple-shaped cloth, GraphNet pna, 15 layers.
+
+    `value` / `via`: the reference's OWN ``FlagModel.rollout`` (src/model/flag.py:194-246: build_graph with its normalisers, predict,
+    second-order integrate, pin the handle nodes, every step) running unchanged on the installed hgn_b200 modules, bf16 processor.
+    `cuda_graph`: the same step (same model object, same normalisers, same arithmetic) captured once in a CUDA graph and replayed --
+    what hgn_b200.graphed offers on top of the drop-in.  `cpu_reference`: FlagModel.rollout of the unmodified reference on the host
+    cores (GPU-less child process), bounded to a few steps."""
+    import hgn_b200
+    shim = _reference_shim()
+    out = {"unit": "rollout steps/s", "steps": ROLLOUT_STEPS,
+           "config": f"{ROLLOUT_W}x{ROLLOUT_H} flag-style cloth ({ROLLOUT_W * ROLLOUT_H} nodes), FlagModel: encoder + {LAYERS} GraphNet layers (pna, bf16 "
+                     f"processor) + decoder, normalisers, {ROLLOUT_STEPS} closed-loop steps"}
+    if not shim.available():
+        out["value"] = None
+        out["via"] = "unavailable: no reference tree (oracle/_ref not staged)"
+        return out
+    shim._install_stub_modules()
+    if shim.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, shim.REFERENCE_ROOT)
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    hgn_b200.install_as_reference_modules()
+    from src.model.flag import FlagModel
+    prev_precision = hgn_b200.precision()
+    hgn_b200.set_precision("bf16")
+    try:
+        model, traj = rollout_model_and_trajectory(FlagModel, dev, ROLLOUT_STEPS)
+        model.rollout({k: v[:5] for k, v in traj.items()}, 5)                   # plans, packed weights
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, mse = model.rollout(traj, ROLLOUT_STEPS)
+        torch.cuda.synchronize()
+        out["value"] = ROLLOUT_STEPS / (time.perf_counter() - t0)
+        out["via"] = "FlagModel.rollout"
+        out["finite"] = bool(torch.isfinite(mse).all())
         try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    one_step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                one_step()
-            out["cuda_graph"] = timed(graph.replay, ROLLOUT_STEPS)
-            out["cuda_graph_bitwise_equal_to_eager"] = bool(torch.equal(world, eager_final))
+            from hgn_b200 import graphed
+            out["cuda_graph"] = graphed.flag_rollout_steps_per_second(model, traj, ROLLOUT_STEPS)
         except Exception as exc:                         # capture is an optimisation of the host side only
             out["cuda_graph"] = None
-            out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
-    # CPU oracle on the same model and mesh, bounded to a few steps
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import hgn_oracle as orc
-    weights = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    cw, cp = world0.cpu(), prev0.cpu()
-    cs, cr, cm, cpin, cpt = senders.cpu(), receivers.cpu(), mesh_pos.cpu(), pinned.cpu(), pinned_type.cpu()
-    torch.set_num_threads(os.cpu_count() or 1)
-    steps_cpu = 5
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        for _ in range(steps_cpu):
-            nf, ef = _cloth_features(cw, cp, cm, cpt, cs, cr)
-            acc = orc.mesh_graph_net(weights, "sum", "none", orc.MultiGraph([nf], [orc.EdgeSet("mesh_edges", ef, cs, cr)]))
-            cw, cp = torch.where(cpin, cw, 2 * cw - cp + 0.01 * acc), cw
-        out["cpu_oracle"] = steps_cpu / (time.perf_counter() - t0)
-    out["cpu_cores"] = torch.get_num_threads()
+            out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        hgn_b200.set_precision(prev_precision)
+    ref = _reference_subprocess(["--steps", "1", "--warmup", "1", "--rollout-steps", "10"], timeout=900)
+    if ref is not None and ref.get("rollout"):
+        out["cpu_reference"] = ref["rollout"]
     return out
 
 
@@ -635,40 +647,98 @@ def rollout_bench(dev):
 CPU_SAMPLE_W, CPU_SAMPLE_H, CPU_SAMPLE_LAYERS = 1000, 125, 1
 
 
-def cpu_pass(state, aggregator="sum"):
+def _reference_shim():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import hgn_oracle as orc
-    w, v0, e0, s, r, coef = state
-    for t in w.values():
-        t.grad = None
-    v = v0.clone().requires_grad_(True)
-    ed = e0.clone().requires_grad_(True)
-    out = orc.processor(w, aggregator, "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
-    loss = (out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3
-    loss.backward()
-    return float(loss)
+    import reference_shim
+    return reference_shim
 
 
-def cpu_state(sample=None, aggregator="sum"):
+def cpu_state(sample=None, aggregator="sum", prefer_reference=True):
+    """(step function, directed edges, kind).  kind 'reference': the reference's OWN ``Processor`` / ``GraphNet`` modules
+    (src/migration/processor.py:27-28, graphnet.py:22-84; torch_scatter restated by oracle/reference_shim.py) from /root/reference or
+    the staged oracle/_ref, with device = cpu -- only possible in a process that sees no GPU (src/util.py:9).  kind 'port':
+    oracle/hgn_oracle.py, used when the reference tree is absent or a GPU is visible."""
     torch.set_num_threads(os.cpu_count() or 1)
     w_, h_, batch, layers = sample or (CPU_SAMPLE_W, CPU_SAMPLE_H, 1, CPU_SAMPLE_LAYERS)
     data = build_inputs(w_, h_, layers, aggregator=aggregator, batch=batch)
+    v0, e0, s, r, coef = data["v0"], data["e0"], data["senders"], data["receivers"], data["coef_v"]
+    shim = _reference_shim()
+    if prefer_reference and shim.available() and not torch.cuda.is_available():
+        shim.load()
+        from src.migration.meshgraphnet import MeshGraphNet as RefMeshGraphNet
+        from src.util import EdgeSet as RefEdgeSet, MultiGraph as RefMultiGraph
+        proc = RefMeshGraphNet(output_size=3, latent_size=LATENT, num_layers=2, message_passing_aggregator=aggregator,
+                               message_passing_steps=layers, architecture="none", edge_sets=["mesh_edges"]).processor
+        with torch.no_grad():                   # materialise the LazyLinear parameters on a one-edge graph
+            proc(RefMultiGraph([torch.zeros(2, LATENT)], [RefEdgeSet("mesh_edges", torch.zeros(1, LATENT), torch.zeros(1, dtype=torch.long),
+                                                                     torch.ones(1, dtype=torch.long))]))
+        proc.load_state_dict({k[len("processor."):]: t for k, t in data["weights"].items()})
+        params = list(proc.parameters())
+
+        def step():
+            for p in params:
+                p.grad = None
+            v = v0.clone().requires_grad_(True)
+            ed = e0.clone().requires_grad_(True)
+            out = proc(RefMultiGraph([v], [RefEdgeSet("mesh_edges", ed, s, r)]))
+            loss = (out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3
+            loss.backward()
+            return float(loss)
+        return step, data["e"], "reference"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgn_oracle as orc
     w = {k: t.clone().requires_grad_(True) for k, t in data["weights"].items()}
-    return (w, data["v0"], data["e0"], data["senders"], data["receivers"], data["coef_v"]), data["e"]
+
+    def step():
+        for t in w.values():
+            t.grad = None
+        v = v0.clone().requires_grad_(True)
+        ed = e0.clone().requires_grad_(True)
+        out = orc.processor(w, aggregator, "none", orc.MultiGraph([v], [orc.EdgeSet("mesh_edges", ed, s, r)]))
+        loss = (out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3
+        loss.backward()
+        return float(loss)
+    return step, data["e"], "port"
 
 
-def cpu_baseline(steps=1, sample=None, aggregator="sum"):
-    w_, h_, batch, layers = sample or (CPU_SAMPLE_W, CPU_SAMPLE_H, 1, CPU_SAMPLE_LAYERS)
-    state, e = cpu_state(sample, aggregator)
-    cpu_pass(state, aggregator)          # untimed: first touch / thread pool start
+def _cpu_sample_text(sample, e, aggregator, kind):
+    w_, h_, batch, layers = sample
+    what = ("the reference's own src/migration Processor (unmodified; torch_scatter restated by oracle/reference_shim.py)" if kind == "reference"
+            else "oracle/hgn_oracle.py (torch CPU ops = the reference's own arithmetic)")
+    return (f"{w_}x{h_}" + (f" x {batch}" if batch > 1 else "") + f" mesh of the workload ({e} directed edges), {layers} layer(s), {aggregator}, "
+            f"fwd+bwd, fp32, {what}, all host threads")
+
+
+def cpu_baseline_inprocess(steps=1, sample=None, aggregator="sum"):
+    sample = sample or _sample_override((CPU_SAMPLE_W, CPU_SAMPLE_H, 1, CPU_SAMPLE_LAYERS))
+    step, e, kind = cpu_state(sample, aggregator)
+    step()                               # untimed: first touch / thread pool start
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pass(state, aggregator)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": e * layers / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "seconds_per_pass": dt,
-            "sample": f"{w_}x{h_}" + (f" x {batch}" if batch > 1 else "") + f" mesh of the workload ({e} directed edges), {layers} layer(s), {aggregator}, "
-                      "fwd+bwd, fp32, oracle/hgn_oracle.py (torch CPU ops = the reference's own arithmetic)"}
+    return {"value": e * sample[3] / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "seconds_per_pass": dt,
+            "sample": _cpu_sample_text(sample, e, aggregator, kind)}
+
+
+def _reference_subprocess(extra, timeout=900):
+    """`bench.py --impl reference ...` in a child that sees no GPU; returns its JSON line (or None)."""
+    try:
+        run = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference"] + extra, capture_output=True, text=True,
+                             timeout=timeout, env=dict(os.environ, CUDA_VISIBLE_DEVICES="", WANDB_MODE="disabled"))
+        lines = [ln for ln in run.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(lines[-1]) if run.returncode == 0 and lines else None
+    except (subprocess.TimeoutExpired, OSError, ValueError):
+        return None
+
+
+def cpu_baseline(steps=1, sample=None, aggregator="sum", workload="cfg5"):
+    """The CPU arm beside the number: the live reference in a GPU-less child process (kind 'reference'); the oracle port in this
+    process only if that child could not run."""
+    line = _reference_subprocess(["--workload", workload, "--aggregator", aggregator, "--steps", str(steps), "--warmup", "1"])
+    if line is not None and line.get("cpu_baseline"):
+        return line["cpu_baseline"]
+    return cpu_baseline_inprocess(steps, _sample_override(sample) if sample else None, aggregator)
 
 
 def torch_cuda_reference(dev, data, aggregator, layers):
@@ -709,30 +779,61 @@ def torch_cuda_reference(dev, data, aggregator, layers):
         return {"value": None, "error": f"{type(exc).__name__}: {exc}"[:200]}
 
 
+def reference_rollout(steps):
+    """The metric's second half on the reference arm: the reference's own ``FlagModel.rollout`` (src/model/flag.py:194-246) on the
+    CPU -- 40x40 cloth, GraphNet pna, 15 layers (BASELINE.json configs[1]) -- for `steps` closed-loop steps."""
+    shim = _reference_shim()
+    shim.load()
+    os.chdir(shim.REFERENCE_ROOT)
+    from src.model.flag import FlagModel
+    model, traj = rollout_model_and_trajectory(FlagModel, torch.device("cpu"), steps)
+    model.rollout({k: v[:2] for k, v in traj.items()}, 2)        # lazy linears
+    t0 = time.perf_counter()
+    model.rollout(traj, steps)
+    return steps / (time.perf_counter() - t0)
+
+
+def _sample_override(sample):
+    """HGN_BENCH_CPU_SAMPLE=WxH[xBATCH[xLAYERS]] shrinks the CPU sample (tests)."""
+    env = os.environ.get("HGN_BENCH_CPU_SAMPLE")
+    if not env:
+        return sample
+    parts = [int(x) for x in env.split("x")]
+    return tuple(parts + list(sample[len(parts):]))
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    state, e = cpu_state()
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_pass(state)
+    _, _, _, _, default_agg, sample, wl_text = WORKLOADS.get(getattr(args, "workload", "cfg5"), WORKLOADS["cfg5"])
+    sample = _sample_override(sample)
+    aggregator = args.aggregator or default_agg
+    step, e, kind = cpu_state(sample, aggregator)
+    layers = sample[3]
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        step()
     steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_pass(state)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    value = e * CPU_SAMPLE_LAYERS / dt
+    value = e * layers / dt
     cores = torch.get_num_threads()
-    sample = (f"each step = {CPU_SAMPLE_W}x{CPU_SAMPLE_H} sub-mesh of the cfg5 mesh ({e} directed edges), {CPU_SAMPLE_LAYERS} layer, fwd+bwd, "
-              "fp32, oracle port of the reference's torch/torch_scatter path on all host threads")
-    print(json.dumps({
+    sample_text = "each step = " + _cpu_sample_text(sample, e, aggregator, kind)
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (same seeded grid mesh family)",
-        "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, processor fwd+bwd",
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{wl_text}, {WORKLOADS.get(getattr(args, 'workload', 'cfg5'), WORKLOADS['cfg5'])[3]} GraphNet layers, {aggregator} aggregator, processor fwd+bwd",
+                   "sample": sample_text},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_text, "seconds_per_pass": dt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if getattr(args, "rollout_steps", 0) > 0 and kind == "reference":
+        line["rollout"] = {"value": reference_rollout(args.rollout_steps), "unit": "rollout steps/s", "steps": args.rollout_steps, "cores": cores,
+                           "via": "FlagModel.rollout (unmodified reference, CPU)"}
+    print(json.dumps(line))
 
 
 def main():
@@ -744,6 +845,7 @@ def main():
     ap.add_argument("--aggregator", default=None, choices=["sum", "pna"],
                     help="message-passing aggregator (default: the workload's; the headline metric is quoted on 'sum'; 'pna' is the "
                          "reference configs' default)")
+    ap.add_argument("--rollout-steps", type=int, default=0, help="reference arm only: also time FlagModel.rollout for this many steps")
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + ["cfg3"],
                     help="cfg5 = the headline 1M/6M mesh (the bench line); cfg2 / cfg4 = small-mesh batched training shapes; "
                          "cfg3 = HeteroGraphNet on a plateCluster-shaped batch (single GPU)")

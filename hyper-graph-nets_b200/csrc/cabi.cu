@@ -89,25 +89,28 @@ size_t edge_project_backward_workspace_tc(int64_t num_nodes);
 int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
                              float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                           const int32_t* receivers, const void* packed, void* out, void* h1, void* h2, cudaStream_t st);
+                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st);
 size_t edge_update_backward_workspace_tc(int64_t num_edges);
 int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                            const int32_t* receivers, const void* h1, const void* h2, const void* packed, const void* grad_out,
+                            const int32_t* receivers, const void* packed, const void* grad_out,
                             const void* grad_agg, void* grad_edge, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
                             float* gb2, float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 int node_update_forward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* packed, void* q1, void* q2,
-                           void* out, void* h1, void* h2, cudaStream_t st);
+                           void* out, cudaStream_t st);
 size_t node_update_backward_workspace_tc(int64_t num_nodes);
 int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* q1, const void* q2,
-                            const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
+                            const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
                             float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
                             void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-static int check_chunks(const hgn_chunks* ch, const char* who) {
+// An empty row set (rows == 0: an edge set without edges, e.g. deforming_plate world_edges in a frame without contact, plate.py:86-110)
+// comes with NULL sources -- an empty device tensor has no storage -- so the per-chunk pointer check applies to rows > 0 only.
+static int check_chunks(const hgn_chunks* ch, int64_t rows, const char* who) {
   HGN_CHECK_ARG(ch != nullptr, "%s: chunks is NULL", who);
   HGN_CHECK_ARG(ch->n_chunks >= 1 && ch->n_chunks <= HGN_MAX_CHUNKS, "%s: n_chunks=%d outside [1,%d]", who, ch->n_chunks, HGN_MAX_CHUNKS);
-  for (int c = 0; c < ch->n_chunks; ++c) HGN_CHECK_ARG(ch->src[c] != nullptr, "%s: chunk %d has no source", who, c);
+  if (rows > 0)
+    for (int c = 0; c < ch->n_chunks; ++c) HGN_CHECK_ARG(ch->src[c] != nullptr, "%s: chunk %d has no source", who, c);
   return HGN_OK;
 }
 
@@ -144,8 +147,8 @@ extern "C" int hgn_mlp_pack(int dtype, int32_t n_chunks, const float* W0, const 
 
 extern "C" int hgn_mlp_forward(int dtype, int64_t rows, const hgn_chunks* chunks, const void* packed, const void* resid,
                                int64_t resid_row_offset, void* out, void* stream) {
-  if (int rc = check_chunks(chunks, "mlp_forward")) return rc;
   HGN_CHECK_ARG(rows >= 0 && rows < (int64_t(1) << 31), "mlp_forward: rows=%lld", (long long)rows);
+  if (int rc = check_chunks(chunks, rows, "mlp_forward")) return rc;
   if (rows == 0) return HGN_OK;
   HGN_CHECK_ARG(packed && resid && out, "mlp_forward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -164,8 +167,8 @@ extern "C" int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunk
                                 int32_t resid_chunk, void* const* grad_chunk, float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                                 float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-  if (int rc = check_chunks(chunks, "mlp_backward")) return rc;
   HGN_CHECK_ARG(rows >= 0 && rows < (int64_t(1) << 31), "mlp_backward: rows=%lld", (long long)rows);
+  if (int rc = check_chunks(chunks, rows, "mlp_backward")) return rc;
   HGN_CHECK_ARG(packed && workspace && grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta,
                 "mlp_backward: null pointer");
   HGN_CHECK_ARG(rows == 0 || grad_out, "mlp_backward: grad_out is NULL");
@@ -215,14 +218,13 @@ extern "C" int hgn_edge_project_backward(int dtype, int64_t num_nodes, const voi
 }
 
 extern "C" int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                                       const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* h1, void* h2,
+                                       const int32_t* senders, const int32_t* receivers, const void* packed, void* out,
                                        void* stream) {
   HGN_BF16_ONLY("edge_update_forward");
   HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_forward: num_edges=%lld", (long long)num_edges);
   if (num_edges == 0) return HGN_OK;
   HGN_CHECK_ARG(edge && proj_s && proj_r && senders && receivers && packed && out, "edge_update_forward: null pointer");
-  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "edge_update_forward: h1 and h2 must be given together");
-  return edge_update_forward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, out, h1, h2, static_cast<cudaStream_t>(stream));
+  return edge_update_forward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges) {
@@ -231,7 +233,7 @@ extern "C" size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t nu
 }
 
 extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                                        const int32_t* senders, const int32_t* receivers, const void* h1, const void* h2,
+                                        const int32_t* senders, const int32_t* receivers,
                                         const void* packed, const void* grad_out,
                                         const void* grad_agg, void* grad_edge, void* grad_pre0, float* grad_W0, float* grad_b0,
                                         float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, float* grad_gamma,
@@ -240,24 +242,22 @@ extern "C" int hgn_edge_update_backward(int dtype, int64_t num_edges, const void
   HGN_CHECK_ARG(num_edges >= 0 && num_edges < (int64_t(1) << 31), "edge_update_backward: num_edges=%lld", (long long)num_edges);
   HGN_CHECK_ARG(packed && workspace && grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta,
                 "edge_update_backward: null pointer");
-  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "edge_update_backward: h1 and h2 must be given together");
-  HGN_CHECK_ARG(num_edges == 0 || (edge && receivers && grad_edge && grad_pre0 && (h1 || (proj_s && proj_r && senders))),
+  HGN_CHECK_ARG(num_edges == 0 || (edge && receivers && grad_edge && grad_pre0 && proj_s && proj_r && senders),
                 "edge_update_backward: null pointer");
-  return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, h1, h2, packed, grad_out, grad_agg, grad_edge, grad_pre0,
+  return edge_update_backward_tc(num_edges, edge, proj_s, proj_r, senders, receivers, packed, grad_out, grad_agg, grad_edge, grad_pre0,
                                  grad_W0, grad_b0, grad_W1, grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes,
                                  static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* packed,
-                                       void* q1, void* q2, void* out, void* h1, void* h2, void* stream) {
+                                       void* q1, void* q2, void* out, void* stream) {
   HGN_BF16_ONLY("node_update_forward");
   HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "node_update_forward: num_nodes=%lld", (long long)num_nodes);
   HGN_CHECK_ARG(n_agg >= 1 && n_agg <= 4 && aggs != nullptr, "node_update_forward: n_agg=%d outside [1,4]", n_agg);
   if (num_nodes == 0) return HGN_OK;
   for (int j = 0; j < n_agg; ++j) HGN_CHECK_ARG(aggs[j] != nullptr, "node_update_forward: aggregate %d is NULL", j);
   HGN_CHECK_ARG(v && packed && q1 && out && (n_agg <= 2 || q2), "node_update_forward: null pointer");
-  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr), "node_update_forward: h1 and h2 must be given together");
-  return node_update_forward_tc(num_nodes, v, n_agg, aggs, packed, q1, q2, out, h1, h2, static_cast<cudaStream_t>(stream));
+  return node_update_forward_tc(num_nodes, v, n_agg, aggs, packed, q1, q2, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes) {
@@ -266,7 +266,7 @@ extern "C" size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t nu
 }
 
 extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* q1,
-                                        const void* q2, const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v,
+                                        const void* q2, const void* packed, const void* grad_out, void* grad_v,
                                         void* const* grad_aggs, float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1, float* grad_W2,
                                         float* grad_b2, float* grad_gamma, float* grad_beta, void* workspace, size_t workspace_bytes,
                                         void* stream) {
@@ -275,10 +275,9 @@ extern "C" int hgn_node_update_backward(int dtype, int64_t num_nodes, const void
   HGN_CHECK_ARG(n_agg >= 1 && n_agg <= 4 && aggs != nullptr && grad_aggs != nullptr, "node_update_backward: n_agg=%d outside [1,4]", n_agg);
   for (int j = 0; j < n_agg; ++j) HGN_CHECK_ARG(aggs[j] != nullptr && grad_aggs[j] != nullptr, "node_update_backward: aggregate %d is NULL", j);
   HGN_CHECK_ARG(v && packed && grad_out && grad_v && workspace, "node_update_backward: null pointer");
-  HGN_CHECK_ARG((h1 == nullptr) == (h2 == nullptr) && (h1 || (q1 && (n_agg <= 2 || q2))),
-                "node_update_backward: needs the q tables (recompute) or h1 and h2 (stash)");
+  HGN_CHECK_ARG(q1 && (n_agg <= 2 || q2), "node_update_backward: needs the q tables of the forward");
   HGN_CHECK_ARG(grad_W0 && grad_b0 && grad_W1 && grad_b1 && grad_W2 && grad_b2 && grad_gamma && grad_beta, "node_update_backward: null pointer");
-  return node_update_backward_tc(num_nodes, v, n_agg, aggs, q1, q2, h1, h2, packed, grad_out, grad_v, grad_aggs, grad_W0, grad_b0, grad_W1,
+  return node_update_backward_tc(num_nodes, v, n_agg, aggs, q1, q2, packed, grad_out, grad_v, grad_aggs, grad_W0, grad_b0, grad_W1,
                                  grad_b1, grad_W2, grad_b2, grad_gamma, grad_beta, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

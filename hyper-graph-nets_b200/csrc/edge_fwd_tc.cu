@@ -39,7 +39,6 @@ struct EdgeFwdArgs {
   const __nv_bfloat16 *proj_s, *proj_r;     // per-node tables; proj_r may be null
   const int32_t *senders, *receivers;       // null = identity (row i gathers table row i)
   int w0_chunks, w0_chunk0;                 // W0 is [128][128 w0_chunks]; the dense input multiplies chunk w0_chunk0
-  __nv_bfloat16 *h1, *h2;                   // optional [rows,128] stash of the hidden activations for the backward (null = none)
   long long* timeline;                      // development (HGN_TC_ABLATE bit 64): clock64 stamps of block 0, [tile][32]
 };
 
@@ -231,8 +230,6 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
       }
       // ---- P0: H1 = relu(e We^T + Ps[s] + Pr[r] + b0) -> TMEM ------------------------------------------------
-      const int64_t srow = tile_row0(it) + r;              // my row; rows past the end compute on zero-filled input and store nothing
-      const bool stash = a.h1 != nullptr && srow < rows;
       if ((tid & 255) == 0) stamp(it, 8);
       wait_acc(100);
       if ((tid & 255) == 0) stamp(it, 9);
@@ -254,7 +251,6 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
           if (prrow != nullptr) ldg256_l1(prrow + 16 * (k + 2), pb[k & 1]);
         }
         tmem_st8(aop + k * 8, h);
-        if (stash) stg256_cs(a.h1 + srow * kD + hh * 64 + k * 16, h);
       }
       tmem_st_wait();
       fence_before_sync();
@@ -275,7 +271,6 @@ edge_fwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         }
         tmem_st8(aop + cg * 16, h);
         tmem_st8(aop + cg * 16 + 8, h + 8);
-        if (stash) { stg256_cs(a.h2 + srow * kD + hh * 64 + cg * 32, h); stg256_cs(a.h2 + srow * kD + hh * 64 + cg * 32 + 16, h + 8); }
       }
       tmem_st_wait();
       fence_before_sync();
@@ -371,7 +366,7 @@ int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows) {
 }
 
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
-                       const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name, cudaStream_t st) {
+                       const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     uint32_t* dbg = debug_buffer_device();
@@ -390,8 +385,6 @@ int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, cons
   a.receivers = receivers;
   a.w0_chunks = w0_chunks;
   a.w0_chunk0 = w0_chunk0;
-  a.h1 = static_cast<__nv_bfloat16*>(h1);
-  a.h2 = static_cast<__nv_bfloat16*>(h1 != nullptr ? h2 : nullptr);
   const int64_t tiles = ceil_div(rows, kTile);
   const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
   static long long* tl_dev = nullptr;

@@ -822,26 +822,11 @@ int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packe
 
 int make_rows_tensor_map(CUtensorMap* tm, const void* base, int64_t rows);   // edge_fwd_tc.cu
 int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, const void* proj_r, const int32_t* senders, const int32_t* receivers,
-                       const void* packed, int w0_chunks, int w0_chunk0, void* out, void* h1, void* h2, const char* name,
-                       cudaStream_t st);                                                                                  // edge_fwd_tc.cu
-int edge_bwd_g4_launch(int64_t rows, int64_t tiles, int grid, const void* packed, const void* dense, const void* proj_s, const void* proj_r,
-                       const int32_t* senders, const int32_t* receivers, int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg,
-                       void* grad_dense, void* grad_pre0, float* w_partial, float* epi_colpart, float* prod_colpart, const char* name,
-                       cudaStream_t st);                         // edge_bwd_g4_tc.cu (experimental)
-int edge_bwd2_launch(int64_t rows, int64_t tiles, int grid, const void* packed, const void* dense, const void* proj_s, const void* proj_r,
-                     const int32_t* senders, const int32_t* receivers, int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg,
-                     void* grad_dense, void* grad_pre0, float* w_partial, float* epi_colpart, float* prod_colpart, const char* name,
-                     cudaStream_t st);                                                                                    // edge_bwd2_tc.cu
-int stash_backward_launch(int64_t rows, const void* dense, const void* h1, const void* h2, const int32_t* receivers, const void* packed,
-                          int w0_chunks, int w0_chunk0, const void* grad_out, const void* grad_agg, void* grad_dense, void* grad_pre0,
-                          float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
-                          float* w_partial, float* epi_colpart, float* prod_colpart, int grid, const char* name,
-                          cudaStream_t st);                                                                               // edge_bwd_stash_tc.cu
-
+                       const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st);                                                                                  // edge_fwd_tc.cu
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                           const int32_t* receivers, const void* packed, void* out, void* h1, void* h2, cudaStream_t st) {
+                           const int32_t* receivers, const void* packed, void* out, cudaStream_t st) {
   static const bool legacy = getenv("HGN_EDGE_FWD_LEGACY") != nullptr;     // development: the generic tile kernel with a pre-add
-  if (!legacy || h1 != nullptr) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, h1, h2, "edge_fwd_tc", st);
+  if (!legacy) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, "edge_fwd_tc", st);
   hgn_chunks ch{};
   ch.n_chunks = 1;
   ch.src[0] = edge;
@@ -855,7 +840,7 @@ int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj
   return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc_legacy", st);
 }
 
-struct EdgeBwdLayout { size_t w_partial, epi, prod, pair, total; int grid, pair_parts; };
+struct EdgeBwdLayout { size_t w_partial, epi, prod, total; int grid; };
 static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
   EdgeBwdLayout L{};
   const int64_t tiles = ceil_div(rows > 0 ? rows : 1, kTile);
@@ -865,8 +850,6 @@ static EdgeBwdLayout edge_bwd_layout(int64_t rows) {
   L.w_partial = take(size_t(L.grid) * 3 * kD * kD * 4);
   L.epi = take(size_t(L.grid) * 4 * 2 * kD * 4);
   L.prod = take(size_t(L.grid) * 3 * kD * 4);
-  L.pair_parts = tc_pair_wgrad_parts(rows);
-  L.pair = take(size_t(L.pair_parts) * 2 * kD * kD * 4);      // dWe = G0^T e partials of the streaming weight-gradient kernel (two-tile backward)
   L.total = off;
   return L;
 }
@@ -882,44 +865,6 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
   const EdgeBwdLayout L = edge_bwd_layout(rows);
   if (int rc = configure_edge_kernels()) return rc;
   char* ws = static_cast<char*>(workspace);
-  // HGN_EDGE_BWD_INTERLEAVED=1: the experimental two-tile interleaved kernel (edge_bwd2_tc.cu; parity-tested, currently 4.3 ms vs
-  // 3.45 ms per cfg5 layer for the one-tile kernel below: see DESIGN.md s3.2); dWe = G0^T dense then comes from the streaming
-  // weight-gradient kernel.  Read per call so that tests can switch it.
-  const char* inter = getenv("HGN_EDGE_BWD_INTERLEAVED");
-  if (inter != nullptr && inter[0] == '1') {
-    float* w_partial = reinterpret_cast<float*>(ws + L.w_partial);
-    float* epi = reinterpret_cast<float*>(ws + L.epi);
-    float* prod = reinterpret_cast<float*>(ws + L.prod);
-    float* pair = reinterpret_cast<float*>(ws + L.pair);
-    if (int rc = edge_bwd2_launch(rows, ceil_div(rows, kTile), L.grid, packed, dense, proj_s, proj_r, senders, receivers, w0_chunks, w0_chunk0,
-                                  grad_out, grad_agg, grad_dense, grad_pre0, w_partial, epi, prod, name, st)) return rc;
-    if (int rc = tc_pair_wgrad(rows, grad_pre0, dense, nullptr, nullptr, pair, L.pair_parts, st)) return rc;
-    {
-      HGN_TIMED("reduce_weight_partials", st);
-      edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi, prod, L.grid, w0_chunks, w0_chunk0, 1, gW0, gW1, gW2,
-                                                                                gb0, gb1, gb2, ggamma, gbeta);
-      reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(pair, L.pair_parts, 2, 1, gW0, w0_chunks * kD, w0_chunk0 * kD);
-    }
-    HGN_LAUNCH_OK("edge_bwd_reduce");
-    return HGN_OK;
-  }
-  // HGN_EDGE_BWD_TMA_GATHER=1: the experimental variant whose table rows arrive by TMA gather4 (edge_bwd_g4_tc.cu; written after the
-  // round's GPU budget was spent -- compiled, not yet run).  Same partial buffers, same reduction.
-  const char* g4 = getenv("HGN_EDGE_BWD_TMA_GATHER");
-  if (g4 != nullptr && g4[0] == '1') {
-    float* w_partial = reinterpret_cast<float*>(ws + L.w_partial);
-    float* epi = reinterpret_cast<float*>(ws + L.epi);
-    float* prod = reinterpret_cast<float*>(ws + L.prod);
-    if (int rc = edge_bwd_g4_launch(rows, ceil_div(rows, kTile), L.grid, packed, dense, proj_s, proj_r, senders, receivers, w0_chunks, w0_chunk0,
-                                    grad_out, grad_agg, grad_dense, grad_pre0, w_partial, epi, prod, name, st)) return rc;
-    {
-      HGN_TIMED("reduce_weight_partials", st);
-      edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi, prod, L.grid, w0_chunks, w0_chunk0, 0, gW0, gW1, gW2,
-                                                                                gb0, gb1, gb2, ggamma, gbeta);
-    }
-    HGN_LAUNCH_OK("edge_bwd_reduce");
-    return HGN_OK;
-  }
   EdgeBwdArgs a{};
   a.edge = static_cast<const __nv_bfloat16*>(dense);
   a.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
@@ -972,17 +917,11 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
 }
 
 int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
-                            const int32_t* receivers, const void* h1, const void* h2, const void* packed, const void* grad_out,
+                            const int32_t* receivers, const void* packed, const void* grad_out,
                             const void* grad_agg, void* grad_edge, void* grad_pre0, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2,
                             float* gb2, float* ggamma, float* gbeta, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const EdgeBwdLayout L = edge_bwd_layout(num_edges);
   if (workspace_bytes < L.total) { set_error("edge_update_backward: workspace %zu < %zu", workspace_bytes, L.total); return HGN_ERR_WORKSPACE; }
-  if (h1 != nullptr && h2 != nullptr) {
-    char* ws = static_cast<char*>(workspace);
-    return stash_backward_launch(num_edges, edge, h1, h2, receivers, packed, 3, 2, grad_out, grad_agg, grad_edge, grad_pre0, gW0, gb0, gW1, gb1,
-                                 gW2, gb2, ggamma, gbeta, reinterpret_cast<float*>(ws + L.w_partial), reinterpret_cast<float*>(ws + L.epi),
-                                 reinterpret_cast<float*>(ws + L.prod), L.grid, "edge_bwd_stash_tc", st);
-  }
   return projected_backward_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, grad_out, grad_agg, grad_edge, grad_pre0,
                                    gW0, gb0, gW1, gb1, gW2, gb2, ggamma, gbeta, workspace, "edge_bwd_tc", st);
 }
@@ -994,7 +933,7 @@ int edge_update_backward_tc(int64_t num_edges, const void* edge, const void* pro
 // first linear are applied per node row into at most two tables, q1 = agg_1 Wa_1^T (+ agg_2 Wa_2^T) and q2 = agg_3 Wa_3^T (+ agg_4
 // Wa_4^T), which the fused kernel gathers through the identity in the places of Ps[s] and Pr[r].
 int node_update_forward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* packed, void* q1, void* q2,
-                           void* out, void* h1, void* h2, cudaStream_t st) {
+                           void* out, cudaStream_t st) {
   for (int t = 0; t * 2 < n_agg; ++t) {
     LinArgs la{};
     la.n_in = n_agg - 2 * t >= 2 ? 2 : 1;
@@ -1003,7 +942,7 @@ int node_update_forward_tc(int64_t num_nodes, const void* v, int n_agg, const vo
     la.n_out = 1; la.b_mn = 0; la.w0_chunks = 1 + n_agg; la.chunk0 = 1 + 2 * t;
     if (int rc = launch_proj(num_nodes, packed, la, "node_project_fwd", st)) return rc;
   }
-  return edge_fwd_tc_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, 1 + n_agg, 0, out, h1, h2, "node_fwd_tc", st);
+  return edge_fwd_tc_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, 1 + n_agg, 0, out, "node_fwd_tc", st);
 }
 
 struct NodeBwdLayout { size_t edge, g0, partial, total; int parts; };
@@ -1021,7 +960,7 @@ static NodeBwdLayout node_bwd_layout(int64_t n) {
 size_t node_update_backward_workspace_tc(int64_t num_nodes) { return node_bwd_layout(num_nodes).total; }
 
 int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const void* const* aggs, const void* q1, const void* q2,
-                            const void* h1, const void* h2, const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
+                            const void* packed, const void* grad_out, void* grad_v, void* const* grad_aggs,
                             float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2, float* ggamma, float* gbeta,
                             void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const NodeBwdLayout L = node_bwd_layout(num_nodes);
@@ -1029,13 +968,7 @@ int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const v
   char* ws = static_cast<char*>(workspace);
   void* g0 = ws + L.g0;
   const int w0_chunks = 1 + n_agg;
-  if (h1 != nullptr && h2 != nullptr) {
-    const EdgeBwdLayout E = edge_bwd_layout(num_nodes);
-    char* ews = ws + L.edge;
-    if (int rc = stash_backward_launch(num_nodes, v, h1, h2, nullptr, packed, w0_chunks, 0, grad_out, nullptr, grad_v, g0, gW0, gb0, gW1, gb1, gW2,
-                                       gb2, ggamma, gbeta, reinterpret_cast<float*>(ews + E.w_partial), reinterpret_cast<float*>(ews + E.epi),
-                                       reinterpret_cast<float*>(ews + E.prod), E.grid, "node_bwd_stash_tc", st)) return rc;
-  } else if (int rc = projected_backward_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, w0_chunks, 0, grad_out, nullptr,
+  if (int rc = projected_backward_launch(num_nodes, v, q1, n_agg > 2 ? q2 : nullptr, nullptr, nullptr, packed, w0_chunks, 0, grad_out, nullptr,
                                                 grad_v, g0, gW0, gb0, gW1, gb1, gW2, gb2, ggamma, gbeta, ws + L.edge, "node_bwd_tc", st)) {
     return rc;
   }

@@ -35,10 +35,17 @@ def install_as_reference_modules() -> None:
         mod = importlib.import_module(f'hgn_b200.migration.{name}')
         sys.modules[f'src.migration.{name}'] = mod
         setattr(mig, name, mod)
-    ref_util = sys.modules.get('src.util')
     ours = importlib.import_module('hgn_b200.util')
-    if ref_util is not None:
-        # keep the reference's namedtuple classes (its models construct them) and swap the segment op
+    ref_util = sys.modules.get('src.util')
+    if ref_util is None and getattr(src_pkg, '__path__', None):
+        # a reference checkout is importable: keep ITS util module (read_yaml, detach, the namedtuple classes its models and
+        # data loader construct) and swap only the hot-path function.  src/util.py:4 imports torch_scatter at module level; an
+        # installation without it gets our module instead, which re-exports the same public names.
+        try:
+            ref_util = importlib.import_module('src.util')
+        except ImportError:
+            ref_util = None
+    if ref_util is not None and ref_util is not ours:
         ref_util.unsorted_segment_operation = ours.unsorted_segment_operation
     else:
         sys.modules['src.util'] = ours

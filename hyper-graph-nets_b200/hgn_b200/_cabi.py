@@ -14,7 +14,7 @@ HGN_F32 = 0
 HGN_BF16 = 1
 AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN = 1, 2, 4, 8
 HGN_MAX_CHUNKS = 24
-ABI_VERSION = 3            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
+ABI_VERSION = 4            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhgn_b200.so")
 
@@ -50,12 +50,12 @@ SIGNATURES = {
     "hgn_edge_project_forward": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgn_edge_project_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hgn_edge_project_backward": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
-    "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_void_p]),
+    "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p]),
     "hgn_edge_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 20 + [c_void_p, c_size_t, c_void_p]),
-    "hgn_node_update_forward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 6 + [c_void_p]),
+    "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 18 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_node_update_forward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 4 + [c_void_p]),
     "hgn_node_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_node_update_backward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 7 + [POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_node_update_backward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 5 + [POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "hgn_rows_gather": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -41,3 +41,83 @@ class GraphedStep:
     def __call__(self):
         self.graph.replay()
         return self.result
+
+
+class FlagRolloutGraph:
+    """One closed-loop step of the reference's ``FlagModel.rollout`` (src/model/flag.py:194-246: build_graph with the model's
+    normalisers, predict, ``update`` = second-order integration, pin every node that is not NORMAL) captured in ONE CUDA graph and
+    replayed per step.  Same model object, same arithmetic as the eager reference loop; what is left out are its per-step host
+    round trips (``torch.unique`` over the cells, ``F.one_hot``'s ``max()`` read-back, the ``.cpu().numpy()`` copy of the positions at
+    flag.py:234, the normalisers' ``_num_accumulations`` comparison) -- the topology-only work is hoisted into
+    ``graph_building.FlagGraphBuilder``.  ``node_dynamic`` (flag.py:102-115; read only by the intra-cluster sampling of the rmp
+    clusterings) is not computed inside the graph, so ``_node_dynamic_normalizer`` does not advance during a graphed rollout."""
+
+    def __init__(self, model, initial_state, warmup: int = 3):
+        from .graph_building import FlagGraphBuilder
+        from .util import NodeType
+        _cabi.require_cuda(initial_state['world_pos'])
+        self.model = model
+        self.builder = FlagGraphBuilder(model, initial_state)
+        node_type = initial_state['node_type']
+        mask = torch.eq(node_type[:, 0], int(NodeType.NORMAL))
+        self.mask = torch.stack((mask, mask, mask), dim=1)
+        self.cur = initial_state['world_pos'].clone()
+        self.prev = initial_state['prev|world_pos'].clone()
+        cur0, prev0 = self.cur.clone(), self.prev.clone()
+
+        def step():
+            inputs = {'world_pos': self.cur, 'prev|world_pos': self.prev}
+            graph = self.builder(inputs, False, node_dynamic=False)
+            prediction = model.update(inputs, model(graph))
+            nxt = torch.where(self.mask, torch.squeeze(prediction), torch.squeeze(self.cur))
+            self.prev.copy_(self.cur)
+            self.cur.copy_(nxt)
+
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            self.cur.copy_(cur0)
+            self.prev.copy_(prev0)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                step()
+            self.cur.copy_(cur0)
+            self.prev.copy_(prev0)
+
+    def reset(self, world_pos: torch.Tensor, prev_world_pos: torch.Tensor) -> None:
+        self.cur.copy_(world_pos)
+        self.prev.copy_(prev_world_pos)
+
+    @torch.no_grad()
+    def rollout(self, num_steps: int) -> torch.Tensor:
+        """``pred_pos [num_steps, N, 3]`` exactly as ``FlagModel.rollout`` stacks it (the position BEFORE each step, flag.py:244)."""
+        out = torch.empty((num_steps,) + tuple(self.cur.shape), dtype=self.cur.dtype, device=self.cur.device)
+        for i in range(num_steps):
+            out[i].copy_(self.cur)
+            self.graph.replay()
+        return out
+
+
+def flag_rollout_steps_per_second(model, traj, steps: int) -> dict:
+    """bench.py helper: the graphed rollout's rate, and its agreement with ``model.rollout`` on the same trajectory."""
+    import time
+    initial_state = {k: torch.squeeze(v, 0)[0] for k, v in traj.items()}
+    runner = FlagRolloutGraph(model, initial_state)
+    check_steps = min(steps, 20)
+    eager, _ = model.rollout({k: v[:check_steps] for k, v in traj.items()}, check_steps)
+    got = runner.rollout(check_steps)
+    ref = eager['pred_pos']
+    travelled = (ref - ref[:1]).abs().max().clamp_min(1e-12)
+    err = float((got - ref).abs().max() / travelled)
+    runner.reset(initial_state['world_pos'], initial_state['prev|world_pos'])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    runner.rollout(steps)
+    torch.cuda.synchronize()
+    return {"value": steps / (time.perf_counter() - t0), "unit": "rollout steps/s", "steps": steps,
+            "max_error_vs_FlagModel_rollout_relative_to_distance_travelled": err, "checked_steps": check_steps,
+            "what": "FlagModel.rollout's step (same model object and normalisers) captured in one CUDA graph per step (hgn_b200.graphed.FlagRolloutGraph)"}

@@ -25,20 +25,6 @@ D_LATENT = 128
 OP_BITS = {"sum": AGG_SUM, "mean": AGG_MEAN, "max": AGG_MAX, "min": AGG_MIN}
 PNA_MASK = AGG_SUM | AGG_MEAN | AGG_MAX | AGG_MIN
 
-# Backward of the projected edge / node updates: 'recompute' (default) saves nothing but the block inputs; 'stash' keeps the
-# two hidden activations of the forward (2 x 256 B per row and layer) so that the backward skips the first two layers and the
-# table gathers.  On cfg5 the stash backward kernel is 0.9 ms faster per layer but the forward pays 0.6 ms for the extra
-# writes and the whole step ends up equal (both are then HBM-traffic bound) at +46 GB of HBM: see DESIGN.md s3.
-import os as _os
-backward_mode = _os.environ.get("HGN_B200_BACKWARD", "recompute")
-
-
-def _stash() -> bool:
-    if backward_mode not in ("stash", "recompute"):
-        raise _cabi.HgnError(f"unknown backward mode {backward_mode!r} (expected 'stash' or 'recompute')")
-    return backward_mode == "stash"
-
-
 # launch counter (bench.py reports "gpu_launches": kernels of ours launched in the timed region)
 launch_count = 0
 
@@ -351,13 +337,10 @@ class _EdgeUpdate(torch.autograd.Function):
         lib = _cabi.load()
         E = e.shape[0]
         out = torch.empty_like(e)
-        stash = _stash() and E > 0 and any(ctx.needs_input_grad)
-        h1 = torch.empty_like(e) if stash else None
-        h2 = torch.empty_like(e) if stash else None
         with torch.cuda.device(e.device):
             _cabi.check(lib.hgn_edge_update_forward(_cabi.HGN_BF16, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(),
-                                                    r_plan.ids32.data_ptr(), packed.data_ptr(), out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2),
-                                                    _cabi.stream_ptr()), "hgn_edge_update_forward")
+                                                    r_plan.ids32.data_ptr(), packed.data_ptr(), out.data_ptr(), _cabi.stream_ptr()),
+                        "hgn_edge_update_forward")
             _count()
             agg = None
             if want_agg:
@@ -366,11 +349,8 @@ class _EdgeUpdate(torch.autograd.Function):
                                                    r_plan.num_segments, agg.data_ptr(), None, None, None, None, None, 0, _cabi.stream_ptr()),
                             "hgn_segment_reduce")
                 _count()
-        if stash:
-            ctx.save_for_backward(e, h1, h2)        # the node tables are not needed again
-        else:
-            ctx.save_for_backward(e, ps, pr)
-        ctx.stash, ctx.n_nodes = stash, ps.shape[0]
+        ctx.save_for_backward(e, ps, pr)              # the hidden activations are recomputed by the backward kernel
+        ctx.n_nodes = ps.shape[0]
         ctx.packed, ctx.s_plan, ctx.r_plan = packed, s_plan, r_plan
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         if want_agg:
@@ -380,12 +360,7 @@ class _EdgeUpdate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, grad_agg):
         lib = _cabi.load()
-        if ctx.stash:
-            e, h1, h2 = ctx.saved_tensors
-            ps = pr = None
-        else:
-            e, ps, pr = ctx.saved_tensors
-            h1 = h2 = None
+        e, ps, pr = ctx.saved_tensors
         s_plan, r_plan = ctx.s_plan, ctx.r_plan
         E, dev = e.shape[0], e.device
         n = ctx.n_nodes
@@ -404,7 +379,7 @@ class _EdgeUpdate(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.hgn_edge_update_backward(
                 _cabi.HGN_BF16, E, e.data_ptr(), _cabi.ptr(ps), _cabi.ptr(pr), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
-                _cabi.ptr(h1), _cabi.ptr(h2), ctx.packed.data_ptr(), _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(),
+                ctx.packed.data_ptr(), _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(),
                 *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_edge_update_backward")
             _count(2)
             # d loss / d Ps, d Pr: sender- and receiver-keyed segment sums of G0 (deterministic CSR passes)
@@ -445,20 +420,14 @@ class _NodeUpdate(torch.autograd.Function):
         q1 = torch.empty_like(v)
         q2 = torch.empty_like(v) if k > 2 else None
         out = torch.empty_like(v)
-        stash = _stash() and any(ctx.needs_input_grad)
-        h1 = torch.empty_like(v) if stash else None
-        h2 = torch.empty_like(v) if stash else None
         agg_ptrs = (ctypes.c_void_p * k)(*[a.data_ptr() for a in aggs])
         with torch.cuda.device(v.device):
             _cabi.check(lib.hgn_node_update_forward(_cabi.HGN_BF16, n, v.data_ptr(), k, agg_ptrs, packed.data_ptr(), q1.data_ptr(),
-                                                    _cabi.ptr(q2), out.data_ptr(), _cabi.ptr(h1), _cabi.ptr(h2), _cabi.stream_ptr()),
+                                                    _cabi.ptr(q2), out.data_ptr(), _cabi.stream_ptr()),
                         "hgn_node_update_forward")
         _count(1 + (k + 1) // 2)
-        if stash:
-            ctx.save_for_backward(v, *aggs, h1, h2)
-        else:
-            ctx.save_for_backward(v, *aggs, q1, *([q2] if q2 is not None else []))
-        ctx.stash, ctx.k = stash, k
+        ctx.save_for_backward(v, *aggs, q1, *([q2] if q2 is not None else []))
+        ctx.k = k
         ctx.packed = packed
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         return out
@@ -469,13 +438,8 @@ class _NodeUpdate(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         k = ctx.k
         v, aggs, rest = saved[0], saved[1:1 + k], saved[1 + k:]
-        if ctx.stash:
-            h1, h2 = rest
-            q1 = q2 = None
-        else:
-            h1 = h2 = None
-            q1 = rest[0]
-            q2 = rest[1] if len(rest) > 1 else None
+        q1 = rest[0]
+        q2 = rest[1] if len(rest) > 1 else None
         n, dev = v.shape[0], v.device
         grad_out = grad_out.contiguous().to(v.dtype)
         grad_v = torch.empty_like(v)
@@ -487,7 +451,7 @@ class _NodeUpdate(torch.autograd.Function):
             ws_bytes = lib.hgn_node_update_backward_workspace_bytes(_cabi.HGN_BF16, n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _cabi.check(lib.hgn_node_update_backward(
-                _cabi.HGN_BF16, n, v.data_ptr(), k, agg_ptrs, _cabi.ptr(q1), _cabi.ptr(q2), _cabi.ptr(h1), _cabi.ptr(h2),
+                _cabi.HGN_BF16, n, v.data_ptr(), k, agg_ptrs, _cabi.ptr(q1), _cabi.ptr(q2),
                 ctx.packed.data_ptr(), grad_out.data_ptr(), grad_v.data_ptr(), gagg_ptrs, *[g.data_ptr() for g in gparams],
                 ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_node_update_backward")
         _count(2 + 3 * ((k + 1) // 2))

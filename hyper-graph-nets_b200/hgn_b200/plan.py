@@ -10,12 +10,13 @@ forward and by the deterministic gather backward.
 from __future__ import annotations
 
 from collections import OrderedDict
+import os as _os
+import weakref as _weakref
 
 import torch
 
 from . import _cabi
 
-_CACHE_CAPACITY = 256
 
 
 class SegmentPlan:
@@ -25,30 +26,43 @@ class SegmentPlan:
     ``perm``   element ids grouped by segment, ascending id inside a segment (stable).
     ``rowptr`` ``rowptr[s]:rowptr[s+1]`` delimits segment ``s`` inside ``perm``."""
 
-    __slots__ = ("ids", "key_tensor", "num_segments", "num_elements", "_perm", "_rowptr", "ids32", "version")
+    __slots__ = ("_ids_ref", "_ids_own", "num_segments", "num_elements", "_perm", "_rowptr", "ids32", "version", "__weakref__")
 
     def __init__(self, ids: torch.Tensor, num_segments: int):
         _cabi.require_cuda(ids)
-        if ids.dtype != torch.int64:
-            ids = ids.to(torch.int64)
-        self.ids = ids.contiguous()
-        self.key_tensor = None
         self.version = ids._version
+        # The caller's tensor is referenced weakly (the cache entry of this plan must die with it); a converted copy is ours.
+        if ids.dtype == torch.int64 and ids.is_contiguous():
+            self._ids_ref, self._ids_own = _weakref.ref(ids), None
+        else:
+            self._ids_ref, self._ids_own = None, ids.to(torch.int64).contiguous()
         self.num_segments = int(num_segments)
-        self.num_elements = self.ids.numel()
-        self.ids32 = self.ids.to(torch.int32) if self.num_elements else torch.zeros(1, dtype=torch.int32, device=ids.device)
+        self.num_elements = ids.numel()
+        self.ids32 = ids.to(torch.int32).contiguous() if self.num_elements else torch.zeros(1, dtype=torch.int32, device=ids.device)
         self._perm = None
         self._rowptr = None
 
+    @property
+    def ids(self) -> torch.Tensor:
+        """The int64 index vector (the caller's own tensor while it is alive, else widened from ``ids32``)."""
+        if self._ids_own is not None:
+            return self._ids_own
+        t = self._ids_ref() if self._ids_ref is not None else None
+        if t is None or t._version != self.version:
+            self._ids_own = self.ids32[:self.num_elements].to(torch.int64)
+            return self._ids_own
+        return t
+
     def _build_csr(self) -> None:
         lib = _cabi.load()
-        E, dev = self.num_elements, self.ids.device
+        ids = self.ids
+        E, dev = self.num_elements, ids.device
         self._perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self._rowptr = torch.empty(self.num_segments + 1, dtype=torch.int32, device=dev)
         ws_bytes = lib.hgn_csr_workspace_bytes(E, self.num_segments)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _cabi.check(lib.hgn_csr_build(self.ids.data_ptr(), E, self.num_segments, self._perm.data_ptr(),
+            _cabi.check(lib.hgn_csr_build(ids.data_ptr(), E, self.num_segments, self._perm.data_ptr(),
                                           self._rowptr.data_ptr(), None, ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
                         "hgn_csr_build")
 
@@ -65,41 +79,79 @@ class SegmentPlan:
         return self._rowptr
 
 
-_plans: "OrderedDict[tuple, object]" = OrderedDict()
+# ---- cache -------------------------------------------------------------------------------------------------------------------
+# Keyed on the IDENTITY of the index tensor object (id + a weak reference that must still resolve to that very object) and its
+# in-place version counter -- never on (data_ptr, numel): two strided views of one buffer share those, and a freed buffer's address
+# is recycled.  An entry holds only a weak reference to its source tensor: when the caller drops the tensor (the reference's
+# build_graph / _get_batched create fresh index tensors every step) the entry is dead and is swept at the next insertion.  Live
+# entries are bounded in BYTES (HGN_PLAN_CACHE_BYTES, default 4 GiB; least recently used first), not in count.
+_CACHE_BYTES = int(_os.environ.get("HGN_PLAN_CACHE_BYTES", str(4 << 30)))
+_plans: "OrderedDict[tuple, tuple]" = OrderedDict()      # key -> (weakrefs to the source tensors, versions, value, bytes)
+_plan_bytes = 0
 
 
-def _remember(key, value) -> None:
-    _plans[key] = value
-    if len(_plans) > _CACHE_CAPACITY:
-        _plans.popitem(last=False)
+def _tensor_bytes(*tensors) -> int:
+    return sum(t.numel() * t.element_size() for t in tensors if isinstance(t, torch.Tensor))
+
+
+def _lookup(key, sources):
+    hit = _plans.get(key)
+    if hit is None:
+        return None
+    refs, versions, value, _ = hit
+    if any(r() is not t for r, t in zip(refs, sources)) or versions != tuple(t._version for t in sources):
+        _forget(key)
+        return None
+    _plans.move_to_end(key)
+    return value
+
+
+def _forget(key) -> None:
+    global _plan_bytes
+    hit = _plans.pop(key, None)
+    if hit is not None:
+        _plan_bytes -= hit[3]
+
+
+def _remember(key, sources, value, nbytes: int) -> None:
+    global _plan_bytes
+    for k in [k for k, (refs, _, _, _) in _plans.items() if any(r() is None for r in refs)]:     # sources that have died
+        _forget(k)
+    _forget(key)
+    _plans[key] = (tuple(_weakref.ref(t) for t in sources), tuple(t._version for t in sources), value, int(nbytes))
+    _plan_bytes += int(nbytes)
+    while _plan_bytes > _CACHE_BYTES and len(_plans) > 1:
+        _forget(next(iter(_plans)))
+
+
+def plan_cache_stats() -> dict:
+    return {"entries": len(_plans), "bytes": _plan_bytes, "limit_bytes": _CACHE_BYTES}
 
 
 def segment_plan(ids: torch.Tensor, num_segments: int) -> SegmentPlan:
-    """Cached plan for a device index tensor.  The key is the tensor's storage identity (+ in-place
-    version counter); the cache entry keeps the tensor alive so its address cannot be recycled."""
-    key = ("plan", ids.data_ptr(), ids.numel(), int(num_segments), ids.device.index, ids.dtype)
-    hit = _plans.get(key)
-    if hit is not None and hit.version == ids._version:
-        _plans.move_to_end(key)
+    """Cached plan for a device index tensor (see the cache notes above).  Callers with a dynamic set (``world_edges`` changes every
+    step) simply pass each step's fresh tensor: its plan lives exactly as long as the tensor does."""
+    key = ("plan", id(ids), int(num_segments))
+    hit = _lookup(key, (ids,))
+    if hit is not None:
         return hit
     plan = SegmentPlan(ids, num_segments)
-    plan.key_tensor = ids
-    plan.version = ids._version
-    _remember(key, plan)
+    # ids (int64, a private copy unless the caller's tensor already was contiguous int64) + ids32 + perm + rowptr
+    # ids32 + perm + rowptr (+ a private int64 copy when the caller's tensor was not contiguous int64)
+    _remember(key, (ids,), plan, ids.numel() * 8 + (int(num_segments) + 1) * 4 + (ids.numel() * 8 if plan._ids_own is not None else 0))
     return plan
 
 
 def to_device_index(ids: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """Device copy of an index tensor, made once per source tensor."""
+    """Device copy of an index tensor, made once per source tensor object."""
     if ids.device == device:
         return ids
-    key = ("h2d", ids.data_ptr(), ids.numel(), str(device), ids.dtype)
-    hit = _plans.get(key)
-    if hit is not None and hit[2] == ids._version:
-        _plans.move_to_end(key)
-        return hit[1]
+    key = ("h2d", id(ids), str(device))
+    hit = _lookup(key, (ids,))
+    if hit is not None:
+        return hit
     dev_ids = ids.to(device)
-    _remember(key, (ids, dev_ids, ids._version))
+    _remember(key, (ids,), dev_ids, _tensor_bytes(dev_ids))
     return dev_ids
 
 
@@ -137,15 +189,16 @@ class EdgeStorageOrder:
 
 def edge_storage_order(senders: torch.Tensor, receivers: torch.Tensor) -> EdgeStorageOrder:
     """Cached per (senders, receivers) tensor pair, like ``segment_plan``."""
-    key = ("order", senders.data_ptr(), receivers.data_ptr(), receivers.numel(), str(receivers.device))
-    hit = _plans.get(key)
-    if hit is not None and hit[2].version == (senders._version, receivers._version):
-        _plans.move_to_end(key)
-        return hit[2]
+    key = ("order", id(senders), id(receivers))
+    hit = _lookup(key, (senders, receivers))
+    if hit is not None:
+        return hit
     order = EdgeStorageOrder(senders, receivers)
-    _remember(key, (senders, receivers, order))
+    _remember(key, (senders, receivers), order, _tensor_bytes(order.perm, order.inverse, order.senders, order.receivers))
     return order
 
 
 def clear_plan_cache() -> None:
+    global _plan_bytes
     _plans.clear()
+    _plan_bytes = 0

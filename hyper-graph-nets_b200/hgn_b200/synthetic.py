@@ -119,6 +119,41 @@ def plate_frame(plate=(9, 9, 2), obstacle=(4, 4, 2), spacing: float = 0.02, gap:
     }
 
 
+def cylinder_frame(width: int, height: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """One cylinder_flow-style Eulerian frame (cfg 4): a triangulated ``width x height`` rectangle whose first
+    column is INFLOW (4), last column OUTFLOW (5), first / last row and a block in the middle (the obstacle's rim)
+    WALL_BOUNDARY (6), everything else NORMAL (0), so that all four types of src/model/cylinder.py:71-75 occur.
+    ``velocity[N,2], target|velocity[N,2], pressure[N,1]`` are seeded noise around a uniform inflow."""
+    rng = np.random.default_rng(seed)
+    n = width * height
+    jj, ii = np.meshgrid(np.arange(width), np.arange(height))
+    jj, ii = jj.ravel(), ii.ravel()
+    mesh_pos = 0.05 * np.stack([jj, ii], 1).astype(np.float32)
+    node_type = np.zeros((n, 1), np.int32)
+    node_type[(ii == 0) | (ii == height - 1), 0] = 6
+    block = (abs(jj - width // 4) <= 1) & (abs(ii - height // 2) <= 1)
+    node_type[block, 0] = 6
+    node_type[jj == 0, 0] = 4
+    node_type[jj == width - 1, 0] = 5
+    velocity = (np.asarray([1.0, 0.0], np.float32) + 0.1 * rng.standard_normal((n, 2))).astype(np.float32)
+    target = (velocity + 0.01 * rng.standard_normal((n, 2))).astype(np.float32)
+    pressure = (0.5 * rng.standard_normal((n, 1))).astype(np.float32)
+    return {
+        "cells": torch.from_numpy(grid_triangles(width, height)),
+        "mesh_pos": torch.from_numpy(mesh_pos),
+        "node_type": torch.from_numpy(node_type),
+        "velocity": torch.from_numpy(velocity),
+        "target|velocity": torch.from_numpy(target),
+        "pressure": torch.from_numpy(pressure),
+    }
+
+
+def trajectory(frames: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """``[T, N, .]`` tensors per key from T frames of one mesh: the dict ``model.rollout`` takes (src/model/flag.py:194-197; static
+    fields tiled over T like src/data/preprocessing.py:52-53)."""
+    return {key: torch.stack([f[key] for f in frames], 0) for key in frames[0]}
+
+
 # ----------------------------------------------------------------------------------------------
 # deterministic tensors
 # ----------------------------------------------------------------------------------------------

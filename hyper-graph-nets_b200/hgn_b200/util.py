@@ -23,6 +23,25 @@ MultiGraphWithPos = collections.namedtuple('MultiGraph', ['node_features', 'edge
                                                           'unnormalized_edges', 'obstacle_nodes'])
 
 
+def detach(tensor: torch.Tensor):
+    """src/util.py:19-24: a tensor as a numpy array, from either device."""
+    return tensor.detach().cpu().numpy()
+
+
+def read_yaml(config_name: str):
+    """src/util.py:38-47: the 'DEFAULT' document of ``configs/<config_name>.yaml`` (path relative to the working directory,
+    like the reference); ``None`` after printing the parser's message for a malformed file."""
+    import yaml
+    with open(f'configs/{config_name}.yaml', 'r') as stream:
+        try:
+            for document in yaml.safe_load_all(stream):
+                if document['name'] == 'DEFAULT':
+                    return document
+        except yaml.YAMLError as err:
+            print(err)
+            return None
+
+
 class NodeType(enum.IntEnum):  # src/util.py:27-35
     NORMAL = 0
     OBSTACLE = 1

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HGN_B200_ABI_VERSION 3
+#define HGN_B200_ABI_VERSION 4
 
 typedef enum {
   HGN_OK = 0,
@@ -158,12 +158,8 @@ size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t num_nodes);
 int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed,
                               const void* grad_s, const void* grad_r, void* grad_v, float* grad_W0,
                               void* workspace, size_t workspace_bytes, void* stream);
-/* h1 / h2 (both or neither; bf16 [E,128], caller-owned) receive the two hidden activations relu(pre0) and
- * relu(H1 W1^T + b1).  Handing them to the backward replaces its recomputation of the first two layers (and its
- * gathers of the node tables) by two tile loads: a memory-for-time trade (2 x 256 B per edge). */
 int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                            const int32_t* senders, const int32_t* receivers, const void* packed, void* out,
-                            void* h1, void* h2, void* stream);
+                            const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* stream);
 /* Backward (activations recomputed).  The incoming gradient of e' is  grad_out[e] + grad_agg[receivers[e]] :
  * grad_out[E,128] (may be NULL) is the dense part (next layer / loss), grad_agg[N,128] (may be NULL) the gradient
  * of the 'sum' aggregate of e' over receivers (graphnet.py:50-70), gathered here instead of being expanded to
@@ -172,9 +168,8 @@ int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, cons
  * the inputs of hgn_edge_project_backward; grad_W0 columns 256:384 (= We) only; all other parameter gradients
  * complete (fp32, overwritten, fixed-order reductions). */
 size_t hgn_edge_update_backward_workspace_bytes(int dtype, int64_t num_edges);
-/* With h1 / h2 from the forward (both non-NULL) proj_s, proj_r and senders are not read and may be NULL. */
 int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
-                             const int32_t* senders, const int32_t* receivers, const void* h1, const void* h2, const void* packed,
+                             const int32_t* senders, const int32_t* receivers, const void* packed,
                              const void* grad_out, const void* grad_agg, void* grad_edge, void* grad_pre0,
                              float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,
@@ -185,14 +180,14 @@ int hgn_edge_update_backward(int dtype, int64_t num_edges, const void* edge, con
  * n_agg = 1 ('sum', 'mean', 'max' or 'min') or 4 ('pna': sum, mean, max, min in the order of graphnet.py:53-64); aggs[j] is [N,128] bf16.
  * `packed` is the hgn_mlp_pack blob of the node MLP with n_chunks = 1 + n_agg.  q1 (and q2 when n_agg > 2; caller-owned [N,128] bf16)
  * receive agg_1 Wa_1^T + agg_2 Wa_2^T and agg_3 Wa_3^T + agg_4 Wa_4^T; the recompute backward reads them again.  Runs on the projected
- * edge kernels: the q tables play the roles of the node tables, gathered through the identity.  h1 / h2: optional stash, as above.
+ * edge kernels: the q tables play the roles of the node tables, gathered through the identity.
  * Backward: grad_v = d loss / d v (residual branch included), grad_aggs[j] = d loss / d agg_j, and every parameter gradient (fp32,
  * overwritten, fixed-order reductions).  num_nodes must be > 0 for the backward. */
 int hgn_node_update_forward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs, const void* packed,
-                            void* q1, void* q2, void* out, void* h1, void* h2, void* stream);
+                            void* q1, void* q2, void* out, void* stream);
 size_t hgn_node_update_backward_workspace_bytes(int dtype, int64_t num_nodes);
 int hgn_node_update_backward(int dtype, int64_t num_nodes, const void* v, int32_t n_agg, const void* const* aggs,
-                             const void* q1, const void* q2, const void* h1, const void* h2, const void* packed,
+                             const void* q1, const void* q2, const void* packed,
                              const void* grad_out, void* grad_v, void* const* grad_aggs,
                              float* grad_W0, float* grad_b0, float* grad_W1, float* grad_b1,
                              float* grad_W2, float* grad_b2, float* grad_gamma, float* grad_beta,

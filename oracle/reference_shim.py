@@ -1,9 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *live* reference (CemOezcan/hyper-graph-nets).
 
-Only usable in the build container where ``/root/reference`` is mounted; the GPU box never has it, so
-nothing under ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call into this file.  It is used by
-``tests/golden/make_golden.py`` (to produce the committed golden vectors) and by the ``not gpu`` tests
-that cross-check ``oracle/hgn_oracle.py`` against the reference when the mount exists.
+``/root/reference`` is mounted only in the build container.  ``oracle/make_ref.sh`` (run by ``__graft_entry__.build()``
+there) stages the reference's unmodified Python packages under the git-ignored ``oracle/_ref/``, which travels to the
+GPU box with the snapshot like a built ``.so``; this loader takes the mount when present and ``oracle/_ref`` otherwise.
+Nothing at run time reads ``/root/reference`` on the GPU box.  Users: ``tests/golden/make_golden*.py`` (golden vectors),
+the ``not gpu`` tests that cross-check ``oracle/hgn_oracle.py``, the ``-m gpu`` drop-in tests (the reference's own
+``FlagModel`` / ``PlateModel`` / ``CylinderModel`` on the CPU as the checker) and ``bench.py``'s reference arm /
+``cpu_baseline`` (kind "reference").  Never the product path.
 
 The reference imports a handful of packages that are absent from this image.
 They are replaced by in-memory stub modules *before* anything from ``/root/reference/src`` is imported:
@@ -25,7 +28,20 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("HGN_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _find_root() -> str:
+    env = os.environ.get("HGN_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isdir(os.path.join(cand, "src", "migration")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

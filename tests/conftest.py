@@ -14,7 +14,9 @@ for p in (os.path.join(ROOT, "hyper-graph-nets_b200"), os.path.join(ROOT, "oracl
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 MODEL_CASES = ["mgn_sum_L2", "mgn_pna_L1", "mgn_max_L1", "repeated_sum_L1", "multi_mean_L1",
-               "hgn_hyper_pna_L1", "hgn_hyper_sum_L2", "hgn_hetero_pna_L1", "hgn_multiscale_sum_L1"]
+               "hgn_hyper_pna_L1", "hgn_hyper_sum_L2", "hgn_hetero_pna_L1", "hgn_multiscale_sum_L1",
+               # 300 nodes / 16 clusters / 13 mesh-edge tiles (round 2): the remote architectures above one 128-row tile
+               "hgn_hyper_pna_L2_300", "hgn_hetero_pna_L2_300", "hgn_multiscale_pna_L1_300"]
 
 
 def pytest_configure(config):

@@ -14,21 +14,44 @@ import bench  # noqa: E402
 
 
 def test_cpu_baseline_and_reference_arm_contract(monkeypatch, capsys):
-    monkeypatch.setattr(bench, "CPU_SAMPLE_W", 60)
-    monkeypatch.setattr(bench, "CPU_SAMPLE_H", 20)
-    cpu = bench.cpu_baseline(steps=1)
-    assert cpu["kind"] == "port" and cpu["unit"] == bench.UNIT and cpu["value"] > 0 and cpu["cores"] >= 1 and "sample" in cpu
+    """The reference arm runs the LIVE reference's Processor (kind 'reference') when a reference tree is present and no GPU is visible,
+    the oracle port (kind 'port') otherwise; `cpu_baseline` of the GPU arm gets the same object from a GPU-less child process."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_shim
+    want_kind = "reference" if reference_shim.available() and not torch.cuda.is_available() else "port"
+    monkeypatch.setenv("HGN_BENCH_CPU_SAMPLE", "60x20")
+    cpu = bench.cpu_baseline(steps=1)                    # child process: python bench.py --impl reference
+    assert cpu["kind"] in ("reference", "port") and cpu["unit"] == bench.UNIT and cpu["value"] > 0 and cpu["cores"] >= 1
+    assert "60x20" in cpu["sample"]
+    if reference_shim.available():
+        assert cpu["kind"] == "reference"
+    port = bench.cpu_baseline_inprocess(steps=1)
+    assert port["kind"] == want_kind and port["value"] > 0
     monkeypatch.delenv("RANK", raising=False)
-    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=1, impl="reference", aggregator="sum"))
+    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=1, impl="reference", aggregator="sum", workload="cfg5", rollout_steps=0))
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
     assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # ranks other than 0 print nothing
     monkeypatch.setenv("RANK", "1")
-    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=2, impl="reference", aggregator="sum"))
+    bench.run_reference(argparse.Namespace(steps=1, warmup=1, gpus=2, impl="reference", aggregator="sum", workload="cfg5", rollout_steps=0))
     assert capsys.readouterr().out.strip() == ""
+
+
+def test_reference_processor_equals_oracle_port_on_the_bench_sample(monkeypatch):
+    """The two CPU arms compute the same thing: one step's loss of the live reference Processor == the oracle port's."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_shim
+    if not reference_shim.available() or torch.cuda.is_available():
+        import pytest
+        pytest.skip("needs the reference tree and no visible GPU")
+    ref_step, e1, kind = bench.cpu_state((30, 20, 1, 2), "pna")
+    port_step, e2, kind2 = bench.cpu_state((30, 20, 1, 2), "pna", prefer_reference=False)
+    assert (kind, kind2) == ("reference", "port") and e1 == e2
+    a, b = ref_step(), port_step()
+    assert abs(a - b) <= 1e-5 * abs(b)
 
 
 def test_roofline_accounting_of_the_projected_kernels():

@@ -56,7 +56,8 @@ def test_model_matches_reference_golden(name, precision):
         assert rel_err(t, case.arr(f"proc_node_{i}")) < tol, f"node latents {i}"
     assert [es.name for es in latent_out.edge_sets] == case.meta["proc_edge_sets"]
     for es in latent_out.edge_sets:
-        assert rel_err(es.features, case.arr(f"proc_edge_{es.name}")) < tol, es.name
+        if f"proc_edge_{es.name}" in case.z:       # the 300-node fixtures leave the mesh-edge latents out (size)
+            assert rel_err(es.features, case.arr(f"proc_edge_{es.name}")) < tol, es.name
     coef = synthetic.seeded_tensor("loss_coef", out.shape, 3).cuda()
     (out * coef).sum().backward()
     gtol = GRAD_TOL[precision]
@@ -282,14 +283,11 @@ def _bf16_emulated_projected_edge(v, e, s, r, w):
     return e + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
 
 
-@pytest.mark.parametrize("mode", ["stash", "recompute"])
 @pytest.mark.parametrize("want_agg", [False, True])
 @pytest.mark.parametrize("rows,n_nodes", [(1, 5), (63, 40), (128, 64), (129, 33), (1000, 300), (9282, 1600), (200000, 40000)])
-def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg, mode, monkeypatch):
+def test_projected_edge_update_vs_bf16_emulation(rows, n_nodes, want_agg):
     """ops.edge_update (node projection + fused edge forward/backward kernels with the aggregate's gradient gathered in
-    the kernel) against torch arithmetic with the same rounding points, on ragged tile counts, for both backward modes
-    (hidden activations stashed by the forward / recomputed)."""
-    monkeypatch.setattr(ops, "backward_mode", mode)
+    the kernel) against torch arithmetic with the same rounding points, on ragged tile counts."""
     torch.manual_seed(rows + int(want_agg))
     w = _random_mlp_weights(3, 11)
     params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
@@ -335,14 +333,12 @@ def _bf16_emulated_projected_node(v, aggs, w):
     return v + torch.nn.functional.layer_norm(rd(h) @ rd(W2).t() + b2, (128,), g, b, 1e-5)
 
 
-@pytest.mark.parametrize("mode", ["stash", "recompute"])
 @pytest.mark.parametrize("n_agg", [1, 2, 3, 4])
 @pytest.mark.parametrize("n_nodes", [1, 63, 129, 1600, 40000])
-def test_projected_node_update_vs_bf16_emulation(n_nodes, n_agg, mode, monkeypatch):
+def test_projected_node_update_vs_bf16_emulation(n_nodes, n_agg):
     """ops.node_update (aggregate projections + the fused edge kernels driven with identity indices) against torch arithmetic
     with the same rounding points, on ragged tile counts, for 1..4 aggregates ('sum' ... 'pna'); run twice for bit
-    determinism; both backward modes."""
-    monkeypatch.setattr(ops, "backward_mode", mode)
+    determinism."""
     torch.manual_seed(n_nodes + n_agg)
     w = _random_mlp_weights(1 + n_agg, 13)
     v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
@@ -372,77 +368,6 @@ def test_projected_node_update_vs_bf16_emulation(n_nodes, n_agg, mode, monkeypat
         assert rel_l2(a.grad, b.grad) < 1.5e-2
 
 
-def test_interleaved_backward_kernel_matches_default(monkeypatch):
-    """The experimental two-tile interleaved backward kernel (HGN_EDGE_BWD_INTERLEAVED=1, csrc/edge_bwd2_tc.cu) against the default
-    one-tile kernel: same arithmetic and rounding points, so data gradients agree to bf16 rounding of identical values and
-    weight gradients to fp32 summation order."""
-    monkeypatch.setattr(ops, "backward_mode", "recompute")
-    torch.manual_seed(5)
-    w = _random_mlp_weights(3, 11)
-    n_nodes, rows = 3000, 70001
-    s = torch.randint(0, n_nodes, (rows,), device="cuda")
-    r = torch.randint(0, n_nodes, (rows,), device="cuda")
-    sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
-    v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
-    e0 = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
-    runs = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("HGN_EDGE_BWD_INTERLEAVED", flag)
-        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
-        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
-        v, e = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
-        out, agg = ops.edge_update(params, {}, v, e, sp, rp, True)
-        (out.float().sum() + (agg.float() ** 2).sum()).backward()
-        runs[flag] = [v.grad, e.grad] + [p.grad for p in params]
-    for a, b in zip(runs["0"], runs["1"]):
-        assert rel_l2(a.float(), b.float()) < 2e-3
-
-
-@pytest.mark.skipif(not os.environ.get("HGN_TEST_EXPERIMENTAL"), reason="experimental kernel that has not run on a GPU yet: set HGN_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("with_pr,with_agg", [(True, True), (True, False), (False, False)])
-def test_tma_gather_backward_kernel_matches_default(with_pr, with_agg, monkeypatch):
-    """The experimental backward kernel whose table rows arrive by TMA gather4 (HGN_EDGE_BWD_TMA_GATHER=1, csrc/edge_bwd_g4_tc.cu)
-    against the default kernel: identical arithmetic on identical values, so the results must be bitwise equal.  (False, False) is the
-    node-update shape: identity gathers of one table, no aggregate gradient.  Not part of the default run until the kernel has been
-    brought up on a GPU (it was written after this round's GPU budget was spent)."""
-    monkeypatch.setattr(ops, "backward_mode", "recompute")
-    torch.manual_seed(6)
-    runs = {}
-    if with_pr:
-        w = _random_mlp_weights(3, 12)
-        n_nodes, rows = 3000, 70001
-        s = torch.randint(0, n_nodes, (rows,), device="cuda")
-        r = torch.randint(0, n_nodes, (rows,), device="cuda")
-        sp, rp = segment_plan(s, n_nodes), segment_plan(r, n_nodes)
-        v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
-        e0 = torch.randn(rows, 128, device="cuda").to(torch.bfloat16)
-    else:
-        w = _random_mlp_weights(2, 13)
-        n_nodes = 40003
-        v0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
-        a0 = torch.randn(n_nodes, 128, device="cuda").to(torch.bfloat16)
-    for flag in ("0", "1"):
-        monkeypatch.setenv("HGN_EDGE_BWD_TMA_GATHER", flag)
-        params = [w[f"m.0.layers.linear_{k}.{p}"].cuda().requires_grad_(True) for k in range(3) for p in ("weight", "bias")]
-        params += [w["m.1.weight"].cuda().requires_grad_(True), w["m.1.bias"].cuda().requires_grad_(True)]
-        if with_pr:
-            v, e = v0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
-            out, agg = ops.edge_update(params, {}, v, e, sp, rp, with_agg)
-            loss = out.float().sum() * 0.5 + (out.float() ** 2).sum()
-            if with_agg:
-                loss = loss + (agg.float() ** 2).sum()
-            loss.backward()
-            runs[flag] = [v.grad, e.grad] + [p.grad for p in params]
-        else:
-            v, ag = v0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
-            out = ops.node_update(params, {}, v, [ag])
-            (out.float() ** 2).sum().backward()
-            runs[flag] = [v.grad, ag.grad] + [p.grad for p in params]
-    for a, b in zip(runs["0"], runs["1"]):
-        assert torch.equal(a, b)
-
-
-@pytest.mark.skipif(not os.environ.get("HGN_TEST_EXPERIMENTAL"), reason="experimental path that has not run on a GPU yet: set HGN_TEST_EXPERIMENTAL=1")
 def test_receiver_sorted_edge_storage_is_transparent():
     """HGN_EDGE_STORAGE=receiver_sorted (plan.EdgeStorageOrder): the bf16 processor keeps its edge rows sorted by receiver between
     entry and exit.  Forward results are bitwise those of the reference order (stable sort: every receiver's rows keep their order);
@@ -473,9 +398,7 @@ def test_receiver_sorted_edge_storage_is_transparent():
     assert rel_l2(b[2].float(), a[2].float()) < 2e-2 and rel_l2(b[3].float(), a[3].float()) < 2e-2
 
 
-@pytest.mark.parametrize("mode", ["stash", "recompute"])
-def test_projected_edge_update_is_deterministic(mode, monkeypatch):
-    monkeypatch.setattr(ops, "backward_mode", mode)
+def test_projected_edge_update_is_deterministic():
     torch.manual_seed(3)
     w = _random_mlp_weights(3, 11)
     s = torch.randint(0, 3000, (20000,), device="cuda")

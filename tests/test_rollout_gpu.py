@@ -94,7 +94,6 @@ def test_rollout_error_curve_vs_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("HGN_TEST_EXPERIMENTAL"), reason="written after the round's GPU budget was spent: set HGN_TEST_EXPERIMENTAL=1")
 def test_graphed_training_step_follows_eager_including_the_optimizer():
     """fwd + bwd + SGD step captured in one CUDA graph (hgn_b200.graphed.GraphedStep) follows the same three eager steps: the
     weight-pack kernels are part of the graph, so every replay sees the weights the previous replay's optimizer step wrote.  The
