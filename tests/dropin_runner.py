@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- one arm of the drop-in parity tests (tests/test_dropin_gpu.py), run as a subprocess because the two
 arms need different ``sys.modules`` (and the reference captures ``src.util.device`` at import time).
 
-    python tests/dropin_runner.py ARM CASE OUT.npz [precision]
+    python tests/dropin_runner.py ARM CASE OUT.npz [precision [REFERENCE.npz]]
 
 ARM ``reference``: the UNMODIFIED reference (``/root/reference`` when mounted, else the staged ``oracle/_ref``; torch_scatter & co
 stubbed by ``oracle/reference_shim.py``) on the CPU -- the caller hides the GPUs so that ``src.util.device`` is ``cpu``.
@@ -12,6 +12,11 @@ CASE ``flag`` (FlagModel, GraphNet pna, 15 layers, 40x40 cloth -- BASELINE.json 
 plateCluster.yaml model section: spectral clustering, 31 clusters, HeteroGraphNet, 5 edge sets incl. world edges; batches of 2
 through the reference's own ``MeshSimulator._get_batched`` -- configs[2]), ``cylinder`` (CylinderModel, GraphNet pna, 5 layers,
 batches of 2 -- configs[3]), ``flag_hyper`` (FlagModel with flag.yaml's spectral + hyper connector, HyperGraphNet).
+
+With REFERENCE.npz (the reference arm's output) the ``ours`` arm first checks that the graphs it built itself have the reference's
+index lists bit for bit and its features to fp32 rounding, and then runs the training steps on the REFERENCE's feature tensors, so
+that the loss / gradient comparison sees identical inputs (the reference's own torch code gives slightly different features on
+the two devices -- its normalisers' E[x^2] - E[x]^2 amplifies the last bit); the rollout always builds its own graphs.
 
 Both arms execute the same script below: accumulate the normalisers on three frames, load weights that are a pure function of the
 state_dict key, two ``training_step`` + ``loss.backward()`` + ``Adam.step()`` iterations (MeshSimulator.py:131-139), then
@@ -90,6 +95,7 @@ def make_frames(case, count):
 def main():
     arm, case, out_path = sys.argv[1:4]
     precision = sys.argv[4] if len(sys.argv) > 4 else "fp32"
+    given = dict(np.load(sys.argv[5])) if len(sys.argv) > 5 else None
     os.environ.setdefault("WANDB_MODE", "disabled")
     os.environ.setdefault("WANDB_SILENT", "true")
     import reference_shim
@@ -156,6 +162,34 @@ def main():
         rec[f"graph_{es.name}_features"] = es.features.detach().cpu().numpy()
     for i, nf in enumerate(g0.node_features):
         rec[f"graph_node_features_{i}"] = nf.detach().cpu().numpy()
+
+    for i in range(warm, total):                                  # the graphs the training steps consume
+        g = graphs[i]
+        for j, nf in enumerate(g.node_features):
+            rec[f"tg{i}_nf{j}"] = nf.detach().cpu().numpy()
+        for es in g.edge_sets:
+            rec[f"tg{i}_ef_{es.name}"] = es.features.detach().cpu().numpy()
+            rec[f"tg{i}_es_{es.name}"] = np.stack([es.senders.detach().cpu().numpy(), es.receivers.detach().cpu().numpy()]).astype(np.int64)
+    if given is not None:
+        worst = 0.0
+        for i in range(warm, total):
+            g = graphs[i]
+            nfs = []
+            for j, nf in enumerate(g.node_features):
+                want = given[f"tg{i}_nf{j}"]
+                assert want.shape == tuple(nf.shape), (i, j, want.shape, tuple(nf.shape))
+                worst = max(worst, float(np.abs(nf.detach().cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-30)))
+                nfs.append(torch.from_numpy(want).to(device))
+            sets = []
+            for es in g.edge_sets:
+                want = given[f"tg{i}_ef_{es.name}"]
+                assert np.array_equal(rec[f"tg{i}_es_{es.name}"], given[f"tg{i}_es_{es.name}"]), f"graph {i}: {es.name} index lists differ from the reference"
+                assert want.shape == tuple(es.features.shape)
+                if want.size:
+                    worst = max(worst, float(np.abs(es.features.detach().cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-30)))
+                sets.append(es._replace(features=torch.from_numpy(want).to(device)))
+            graphs[i] = g._replace(node_features=nfs, edge_sets=sets)
+        rec["own_graph_feature_error"] = np.asarray(worst)
 
     data = list(zip(graphs[warm:], frames[warm:total]))
     batches = MeshSimulator._get_batched(data, batch) if batch > 1 else data
