@@ -75,20 +75,28 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// Sum over `parts` values `stride` apart in their original order (p = 0, 1, 2, ...: bitwise the sequential sum), with the loads of
-// eight parts in flight at a time -- the dependent load-add chain made these reductions latency-bound (64 us for 148 parts).
+// Sum over `parts` values `stride` apart in a FIXED order (bitwise reproducible run to run): four interleaved partial sums
+// (parts p = 0, 4, 8 ... | 1, 5, 9 ... | ...) with sixteen loads in flight, combined as (s0 + s1) + (s2 + s3).  One sequential chain
+// over 148 per-CTA partials with eight loads in flight was latency-bound (17-19 us per reduction kernel, 1 ms per cfg5 step at every
+// GPU count -- the largest fixed cost of the partitioned runs).
 __device__ __forceinline__ float ordered_sum(const float* __restrict__ src, int parts, int64_t stride) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int p = 0;
-  for (; p + 8 <= parts; p += 8) {
-    float v[8];
+  for (; p + 16 <= parts; p += 16) {
+    float v[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(src + int64_t(p + k) * stride);
+    for (int k = 0; k < 16; ++k) v[k] = __ldg(src + int64_t(p + k) * stride);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += v[k];
+    for (int k = 0; k < 16; k += 4) { s0 += v[k]; s1 += v[k + 1]; s2 += v[k + 2]; s3 += v[k + 3]; }
   }
-  for (; p < parts; ++p) s += __ldg(src + int64_t(p) * stride);
-  return s;
+  for (; p + 4 <= parts; p += 4) {
+    s0 += __ldg(src + int64_t(p) * stride); s1 += __ldg(src + int64_t(p + 1) * stride);
+    s2 += __ldg(src + int64_t(p + 2) * stride); s3 += __ldg(src + int64_t(p + 3) * stride);
+  }
+  if (p < parts) s0 += __ldg(src + int64_t(p) * stride);
+  if (p + 1 < parts) s1 += __ldg(src + int64_t(p + 1) * stride);
+  if (p + 2 < parts) s2 += __ldg(src + int64_t(p + 2) * stride);
+  return (s0 + s1) + (s2 + s3);
 }
 
 }  // namespace hgn

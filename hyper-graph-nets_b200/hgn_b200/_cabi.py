@@ -14,7 +14,7 @@ HGN_F32 = 0
 HGN_BF16 = 1
 AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN = 1, 2, 4, 8
 HGN_MAX_CHUNKS = 24
-ABI_VERSION = 4            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
+ABI_VERSION = 5            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhgn_b200.so")
 
@@ -27,6 +27,19 @@ class Chunks(ctypes.Structure):
         ("idx", c_void_p * HGN_MAX_CHUNKS),
         ("row_offset", c_int64 * HGN_MAX_CHUNKS),
     ]
+
+
+HGN_MAX_PEERS = 16
+
+
+class HaloPeers(ctypes.Structure):
+    """``hgn_halo_peers`` (include/hgn_b200.h)."""
+    _fields_ = [("dst", c_void_p * HGN_MAX_PEERS), ("flag", c_void_p * HGN_MAX_PEERS), ("row_begin", c_int64 * (HGN_MAX_PEERS + 1))]
+
+
+class HaloFlags(ctypes.Structure):
+    """``hgn_halo_flags`` (include/hgn_b200.h)."""
+    _fields_ = [("flag", c_void_p * HGN_MAX_PEERS)]
 
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -58,6 +71,12 @@ SIGNATURES = {
     "hgn_node_update_backward": (c_int, [c_int, c_int64, c_void_p, c_int32, POINTER(c_void_p)] + [c_void_p] * 5 + [POINTER(c_void_p)] + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "hgn_rows_gather": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "hgn_rows_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int, c_void_p]),
+    "hgn_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_char_p]),
+    "hgn_peer_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "hgn_peer_close": (c_int, [c_void_p]),
+    "hgn_peer_free": (c_int, [c_void_p]),
+    "hgn_halo_push": (c_int, [c_int, c_void_p, c_void_p, c_int32, c_void_p, c_int32, ctypes.c_uint32, c_void_p, c_void_p]),
+    "hgn_halo_wait": (c_int, [c_void_p, c_int32, ctypes.c_uint32, c_void_p]),
     "hgn_colsum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hgn_colsum_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "hgn_world_edges_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -119,14 +119,17 @@ class GraphNet(nn.Module):
         return torch.cat(list(features) + aggregates, dim=-1)
 
     # ---- node updates (graphnet.py:34-48, 94-108, 110-124) -------------------------------------
-    def _fused_node_update(self, graph: MultiGraph, edge_sets: List[EdgeSet], model: nn.Module, target: int) -> Tensor:
+    def _fused_node_update(self, graph: MultiGraph, edge_sets: List[EdgeSet], model: nn.Module, target: int,
+                           aggregates: List[Tensor] = None) -> Tensor:
         """``rows' = rows + LN(MLP([rows | agg_1 | ...]))`` for the mesh rows (target 0) or the hyper rows
-        (target 1); aggregates are taken over all ``N + C`` rows like the reference does."""
+        (target 1); aggregates are taken over all ``N + C`` rows like the reference does (``aggregates``: already computed
+        by the caller, when two updates consume the same ones)."""
         node_features = graph.node_features
         offset = 0 if target == 0 else node_features[0].shape[0]
         v = _stack_rows(node_features)
         rows = node_features[target].shape[0]
-        aggregates = self._aggregates(edge_sets, v.shape[0], v.device)
+        if aggregates is None:
+            aggregates = self._aggregates(edge_sets, v.shape[0], v.device)
         sources = [v] + aggregates
         params = _mlp_parameters(model, v.shape[1] * len(sources), v)
         if (1 <= len(aggregates) <= 4 and rows > 0 and v.dtype == torch.bfloat16

@@ -124,8 +124,9 @@ def build_local_graph(senders: torch.Tensor, receivers: torch.Tensor, part: torc
 # halo exchange
 # ------------------------------------------------------------------------------------------------------
 def _gather_rows(src: torch.Tensor, index: torch.Tensor, index32: Optional[torch.Tensor]) -> torch.Tensor:
-    if not src.is_cuda:
-        return src.index_select(0, index)
+    """``src[index]`` through the pack kernel.  CUDA only: the world_size-2 gloo tests install their own CPU stand-ins for this
+    function and ``_scatter_add_rows`` (tests/test_partition_cpu.py) -- the product has no CPU path."""
+    _cabi.require_cuda(src)
     lib = _cabi.load()
     out = torch.empty((index.numel(), src.shape[1]), dtype=src.dtype, device=src.device)
     if index.numel():
@@ -138,30 +139,10 @@ def _scatter_add_rows(dst: torch.Tensor, rows: torch.Tensor, index: torch.Tensor
     """dst[index[i]] += rows[i]; ``index`` has no duplicates (one peer at a time)."""
     if not rows.numel():
         return
-    if not dst.is_cuda:
-        dst.index_add_(0, index, rows)
-        return
+    _cabi.require_cuda(dst, rows)
     lib = _cabi.load()
     _cabi.check(lib.hgn_rows_scatter(_cabi.dtype_code(dst.dtype), rows.data_ptr(), index32.data_ptr(), index.numel(), dst.shape[1],
                                      dst.data_ptr(), 1, _cabi.stream_ptr()), "hgn_rows_scatter")
-
-
-def _exchange_async(send: torch.Tensor, send_splits: Sequence[int], recv_splits: Sequence[int], group):
-    """Starts the all-to-all-v of ``_exchange`` and returns ``(recv, works)`` without waiting: kernels launched on the current
-    stream afterwards run while the rows are in flight; ``work.wait()`` makes the current stream wait for them."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    recv = torch.empty((sum(recv_splits), send.shape[1]), dtype=send.dtype, device=send.device)
-    ops_, so, ro = [], 0, 0
-    for q in range(world):
-        if q != rank and recv_splits[q]:
-            ops_.append(dist.P2POp(dist.irecv, recv[ro:ro + recv_splits[q]], q, group))
-        ro += recv_splits[q]
-    for q in range(world):
-        if q != rank and send_splits[q]:
-            ops_.append(dist.P2POp(dist.isend, send[so:so + send_splits[q]].contiguous(), q, group))
-        so += send_splits[q]
-    return recv, (dist.batch_isend_irecv(ops_) if ops_ else [])
 
 
 def _exchange(send: torch.Tensor, send_splits: Sequence[int], recv_splits: Sequence[int], group) -> torch.Tensor:
@@ -191,7 +172,7 @@ class HaloPlan:
         self.lg = lg
         self.group = group
         self.send_index = lg.send_index.to(device)
-        self.send_index32 = self.send_index.to(torch.int32) if torch.device(device).type == "cuda" else None
+        self.send_index32 = self.send_index.to(torch.int32)
         self.send_splits = list(lg.send_splits)
         self.ghost_splits = list(lg.ghost_splits)
         self.peer_offsets = [0]
@@ -225,184 +206,280 @@ def halo_exchange(owned: torch.Tensor, plan: HaloPlan) -> torch.Tensor:
     return _HaloExchange.apply(owned, plan)
 
 
-class OverlapPlan:
-    """Device-side plans of one rank's share for the overlapped edge update: int32 gather indices, CSR plans of the senders
-    (all local edges, and the cut edges alone) and receivers, and the exchange lists."""
+class _DeviceBytes:
+    """``__cuda_array_interface__`` view of a raw device allocation, for ``torch.as_tensor`` (no copy)."""
 
-    def __init__(self, lg: LocalGraph, halo: "HaloPlan", device):
-        from .plan import segment_plan
-        if lg.n_interior is None:
-            raise ValueError("OverlapPlan needs a LocalGraph built with interior_first=True")
-        self.halo = halo
-        self.n_own, self.n_ghost, self.n_interior = lg.n_own, lg.n_ghost, int(lg.n_interior)
-        self.senders = lg.senders.to(device)
-        self.receivers = lg.receivers.to(device)
-        self.cut_senders = self.senders[self.n_interior:]
-        self.s_plan = segment_plan(self.senders, self.n_own + self.n_ghost)
-        self.r_plan = segment_plan(self.receivers, self.n_own)
-        self.cut_plan = segment_plan(self.cut_senders, self.n_own + self.n_ghost) if self.cut_senders.numel() else None
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-class _PartitionedEdgeUpdate(torch.autograd.Function):
-    """Edge update + 'sum' aggregation of one partitioned ``GraphNet`` block (bf16) with the halo exchange in flight behind the
-    INTERIOR edge tiles: pack boundary rows -> start the NCCL exchange -> project the owned rows and run the fused edge kernel
-    over the edges with an owned sender -> wait -> project the ghost rows and run the kernel over the cut edges.  Backward runs
-    the cut edges first, sends the ghost gradients home, and does the interior edges while those travel."""
+class PeerHalo:
+    """One rank's exchange pool in NVLink peer memory and the mapped pools of its peers (csrc/peer.cu).
+
+    Instead of exchanging the node latents ``v`` of the boundary nodes and projecting the ghosts again on every rank, the owners
+    push the rows of their sender table ``Ps = v Ws^T`` (the only thing an edge kernel reads of a ghost) straight into the ghost
+    part of their peers' tables; in the backward pass the ghost rows of ``segsum_senders(G0)`` go home the same way and are added at
+    the owner in rank order.  A push is one small kernel of the SENDING rank plus a 4-byte flag per peer; the receiving stream
+    waits for its flags with a one-warp kernel.  No NCCL kernel is involved, so nothing competes with the persistent compute
+    kernels for SMs, and nothing returns to the host.
+
+    Pool layout (bytes): ``[flags: 2 directions x world uint32 | push counter | tables: 2 parities x layers x (n_own + n_ghost) rows |
+    inbox: layers x n_send rows]``.  The table of (step parity, layer) is also what the backward pass of that step reads again, so a
+    peer that is one forward pass ahead (it cannot be further: its second layer needs this rank's rows) writes into the other parity."""
+
+    def __init__(self, lg: LocalGraph, layers: int, device, group=None, width: int = 128):
+        import ctypes
+        lib = _cabi.load()
+        self.lg, self.group, self.layers, self.width = lg, group, int(layers), int(width)
+        self.device = torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_own, self.n_ghost, self.n_send = lg.n_own, lg.n_ghost, int(lg.send_index.numel())
+        self.row_bytes = self.width * 2                      # bf16 rows
+        self.rows = self.n_own + self.n_ghost
+        self.off_counter = 2 * self.world * 4
+        self.off_tables = 256 * ((self.off_counter + 4 + 255) // 256)
+        self.off_inbox = self.off_tables + 2 * self.layers * self.rows * self.row_bytes
+        self.nbytes = self.off_inbox + self.layers * max(self.n_send, 1) * self.row_bytes
+        with torch.cuda.device(self.device):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _cabi.check(lib.hgn_peer_alloc(self.nbytes, ctypes.byref(ptr), handle), "hgn_peer_alloc")
+        self.base = int(ptr.value)
+        self.pool = torch.as_tensor(_DeviceBytes(self.base, self.nbytes), device=self.device)
+        info = {"handle": bytes(handle.raw), "n_own": self.n_own, "off_tables": self.off_tables, "off_inbox": self.off_inbox, "rows": self.rows,
+                "n_send": self.n_send, "ghost_splits": list(lg.ghost_splits), "send_splits": list(lg.send_splits)}
+        infos = [None] * self.world
+        dist.all_gather_object(infos, info, group=group)
+        self.peer_base = [0] * self.world
+        self.peer_info = infos
+        with torch.cuda.device(self.device):
+            for q in range(self.world):
+                if q != self.rank and (lg.send_splits[q] or lg.ghost_splits[q]):
+                    mapped = ctypes.c_void_p()
+                    _cabi.check(lib.hgn_peer_open(infos[q]["handle"], ctypes.byref(mapped)), "hgn_peer_open")
+                    self.peer_base[q] = int(mapped.value)
+        self.send_index32 = lg.send_index.to(self.device, dtype=torch.int32)
+        self.ghost_index32 = (self.n_own + torch.arange(self.n_ghost, dtype=torch.int32)).to(self.device)
+        self.send_index = lg.send_index.to(self.device)
+        self.steps_done = 0
+        dist.barrier(group=group)                             # every pool exists and is mapped before anybody pushes
+
+    def close(self) -> None:
+        lib = _cabi.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for q, p in enumerate(self.peer_base):
+            if p:
+                lib.hgn_peer_close(p)
+                self.peer_base[q] = 0
+        if self.base:
+            self.pool = None
+            lib.hgn_peer_free(self.base)
+            self.base = 0
+
+    # ---- views into the own pool -----------------------------------------------------------------------------------
+    def table(self, parity: int, layer: int) -> torch.Tensor:
+        """``[n_own + n_ghost, width]`` bf16: Ps of the owned rows (written here) and of the ghosts (written by their owners)."""
+        off = self.off_tables + (parity * self.layers + layer) * self.rows * self.row_bytes
+        return self.pool[off: off + self.rows * self.row_bytes].view(torch.bfloat16).view(self.rows, self.width)
+
+    def inbox(self, layer: int) -> torch.Tensor:
+        """``[n_send, width]`` bf16: gradients of the rows this rank sent, grouped by the peer that returns them."""
+        off = self.off_inbox + layer * max(self.n_send, 1) * self.row_bytes
+        return self.pool[off: off + self.n_send * self.row_bytes].view(torch.bfloat16).view(self.n_send, self.width)
+
+    # ---- the two exchanges ---------------------------------------------------------------------------------------------
+    def _epoch(self, step: int, layer: int, backward: bool) -> int:
+        return (1 + step * self.layers + (self.layers - 1 - layer if backward else layer)) & 0x7FFFFFFF
+
+    def push_forward(self, step: int, layer: int) -> None:
+        """Boundary rows of this rank's Ps table -> the ghost rows of its peers' tables of the same (parity, layer); then wait for
+        the peers' pushes into this rank's table."""
+        import ctypes
+        lib = _cabi.load()
+        parity, epoch = step & 1, self._epoch(step, layer, False)
+        peers, flags = _cabi.HaloPeers(), _cabi.HaloFlags()
+        n_push = n_wait = 0
+        lo = 0
+        for q in range(self.world):
+            n = self.lg.send_splits[q]
+            if q != self.rank and n:
+                inf = self.peer_info[q]
+                ghost_off = sum(inf["ghost_splits"][:self.rank])
+                peers.dst[n_push] = (self.peer_base[q] + inf["off_tables"]
+                                     + ((parity * self.layers + layer) * inf["rows"] + inf["n_own"] + ghost_off) * self.row_bytes)
+                peers.flag[n_push] = self.peer_base[q] + (0 * self.world + self.rank) * 4
+                peers.row_begin[n_push] = lo
+                n_push += 1
+            lo += n
+            if q != self.rank and self.lg.ghost_splits[q]:
+                flags.flag[n_wait] = self.base + (0 * self.world + q) * 4
+                n_wait += 1
+        peers.row_begin[n_push] = lo
+        self._run(lib, self.table(parity, layer), self.send_index32, peers, n_push, flags, n_wait, epoch, compact=True)
+
+    def push_backward(self, step: int, layer: int, gs: torch.Tensor) -> None:
+        """Ghost rows of ``gs`` (sender-keyed sums of G0, ``[n_own + n_ghost, width]``) -> their owners' inboxes; then wait for the
+        rows the peers return to this rank."""
+        lib = _cabi.load()
+        epoch = self._epoch(step, layer, True)
+        peers, flags = _cabi.HaloPeers(), _cabi.HaloFlags()
+        n_push = n_wait = 0
+        lo = 0
+        for q in range(self.world):
+            n = self.lg.ghost_splits[q]
+            if q != self.rank and n:
+                inf = self.peer_info[q]
+                send_off = sum(inf["send_splits"][:self.rank])
+                peers.dst[n_push] = self.peer_base[q] + inf["off_inbox"] + (layer * max(inf["n_send"], 1) + send_off) * self.row_bytes
+                peers.flag[n_push] = self.peer_base[q] + (1 * self.world + self.rank) * 4
+                peers.row_begin[n_push] = lo
+                n_push += 1
+            lo += n
+            if q != self.rank and self.lg.send_splits[q]:
+                flags.flag[n_wait] = self.base + (1 * self.world + q) * 4
+                n_wait += 1
+        peers.row_begin[n_push] = lo
+        self._run(lib, gs, self.ghost_index32, peers, n_push, flags, n_wait, epoch, compact=False)
+
+    def _run(self, lib, table, index32, peers, n_push, flags, n_wait, epoch, compact):
+        import ctypes
+        # row_begin was filled with offsets into the FULL per-rank ordering; peers without rows were skipped, so the offsets of the
+        # kept ones are already right (rows of a skipped peer do not exist)
+        with torch.cuda.device(self.device):
+            st = _cabi.stream_ptr()
+            _cabi.check(lib.hgn_halo_push(_cabi.HGN_BF16, table.data_ptr(), index32.data_ptr(), self.width, ctypes.byref(peers), n_push, epoch,
+                                          self.base + self.off_counter, st), "hgn_halo_push")
+            _cabi.check(lib.hgn_halo_wait(ctypes.byref(flags), n_wait, epoch, st), "hgn_halo_wait")
+
+
+class _PeerEdgeUpdate(torch.autograd.Function):
+    """Edge update + 'sum' aggregation of one partitioned ``GraphNet`` block (bf16) with the halo in peer memory: project the
+    owned rows into this layer's table, push the boundary rows of ``Ps`` to the peers, wait for theirs, run the fused edge kernel
+    over all local edges.  Backward: fused edge backward, sender- / receiver-keyed sums of G0, ghost rows of the sender sums go
+    home, the returned rows are added at their owners (peers in rank order: deterministic), node-level dgrad / wgrad."""
 
     @staticmethod
-    def forward(ctx, owned, e, W0, b0, W1, b1, W2, b2, gamma, beta, packed, op: OverlapPlan):
-        lib, BF, halo = _cabi.load(), _cabi.HGN_BF16, op.halo
-        No, G, E, Ei = op.n_own, op.n_ghost, e.shape[0], op.n_interior
+    def forward(ctx, owned, e, W0, b0, W1, b1, W2, b2, gamma, beta, packed, halo: PeerHalo, step: int, layer: int):
+        lib, BF = _cabi.load(), _cabi.HGN_BF16
+        No, E = halo.n_own, e.shape[0]
         owned, e = owned.contiguous(), e.contiguous()
-        s32, r32 = op.s_plan.ids32, op.r_plan.ids32
+        ps = halo.table(step & 1, layer)
+        pr = torch.empty((No, owned.shape[1]), dtype=owned.dtype, device=owned.device)
+        out = torch.empty_like(e)
+        s32, r32 = halo.s_plan.ids32, halo.r_plan.ids32
         with torch.cuda.device(owned.device):
             st = _cabi.stream_ptr()
-            send = _gather_rows(owned, halo.send_index, halo.send_index32)
-            ghosts, works = _exchange_async(send, halo.send_splits, halo.ghost_splits, halo.group)
-            ps = torch.empty((No + G, owned.shape[1]), dtype=owned.dtype, device=owned.device)
-            pr = torch.empty_like(ps)
-            out = torch.empty_like(e)
             _cabi.check(lib.hgn_edge_project_forward(BF, No, owned.data_ptr(), packed.data_ptr(), ps.data_ptr(), pr.data_ptr(), st),
                         "hgn_edge_project_forward")
-            if Ei:
-                _cabi.check(lib.hgn_edge_update_forward(BF, Ei, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s32.data_ptr(), r32.data_ptr(),
-                                                        packed.data_ptr(), out.data_ptr(), None, None, st), "hgn_edge_update_forward")
-            for w in works:
-                w.wait()
-            if G:
-                _cabi.check(lib.hgn_edge_project_forward(BF, G, ghosts.data_ptr(), packed.data_ptr(), ps[No:].data_ptr(), pr[No:].data_ptr(), st),
-                            "hgn_edge_project_forward")
-            if E - Ei:
-                _cabi.check(lib.hgn_edge_update_forward(BF, E - Ei, e[Ei:].data_ptr(), ps.data_ptr(), pr.data_ptr(), s32[Ei:].data_ptr(),
-                                                        r32[Ei:].data_ptr(), packed.data_ptr(), out[Ei:].data_ptr(), None, None, st),
-                            "hgn_edge_update_forward")
+            halo.push_forward(step, layer)
+            _cabi.check(lib.hgn_edge_update_forward(BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s32.data_ptr(), r32.data_ptr(),
+                                                    packed.data_ptr(), out.data_ptr(), st), "hgn_edge_update_forward")
             agg = torch.empty((No, owned.shape[1]), dtype=owned.dtype, device=owned.device)
-            _cabi.check(lib.hgn_segment_reduce(BF, out.data_ptr(), E, owned.shape[1], op.r_plan.perm.data_ptr(), op.r_plan.rowptr.data_ptr(), No,
+            _cabi.check(lib.hgn_segment_reduce(BF, out.data_ptr(), E, owned.shape[1], halo.r_plan.perm.data_ptr(), halo.r_plan.rowptr.data_ptr(), No,
                                                agg.data_ptr(), None, None, None, None, None, 0, st), "hgn_segment_reduce")
         from . import ops as _ops
-        _ops._count(6)
-        ctx.save_for_backward(owned, ghosts, e, ps, pr)
-        ctx.op, ctx.packed = op, packed
+        _ops._count(5)
+        ctx.save_for_backward(owned, e, pr)
+        ctx.halo, ctx.packed, ctx.step, ctx.layer = halo, packed, step, layer
         ctx.param_shapes = [tuple(p.shape) for p in (W0, b0, W1, b1, W2, b2, gamma, beta)]
         return out, agg
 
     @staticmethod
     def backward(ctx, grad_out, grad_agg):
-        lib, BF, op = _cabi.load(), _cabi.HGN_BF16, ctx.op
-        halo = op.halo
-        owned, ghosts, e, ps, pr = ctx.saved_tensors
-        No, G, E, Ei = op.n_own, op.n_ghost, e.shape[0], op.n_interior
+        lib, BF, halo = _cabi.load(), _cabi.HGN_BF16, ctx.halo
+        owned, e, pr = ctx.saved_tensors
+        step, layer = ctx.step, ctx.layer
+        ps = halo.table(step & 1, layer)                     # still this step's rows: see PeerHalo
+        No, G, E = halo.n_own, halo.n_ghost, e.shape[0]
         D, dev = owned.shape[1], owned.device
-        s32, r32 = op.s_plan.ids32, op.r_plan.ids32
+        s_plan, r_plan = halo.s_plan, halo.r_plan
         grad_out = grad_out.contiguous().to(e.dtype) if grad_out is not None else None
         grad_agg = grad_agg.contiguous().to(e.dtype) if grad_agg is not None else None
         grad_e, g0 = torch.empty_like(e), torch.empty_like(e)
-
-        def new_gparams():
-            return [torch.zeros(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes]
-
+        gp = [torch.zeros(shape, dtype=torch.float32, device=dev) if i == 0 else torch.empty(shape, dtype=torch.float32, device=dev)
+              for i, shape in enumerate(ctx.param_shapes)]
+        gs = torch.empty((No + G, D), dtype=e.dtype, device=dev)
+        gr = torch.empty((No, D), dtype=e.dtype, device=dev)
+        grad_owned = torch.empty((No, D), dtype=e.dtype, device=dev)
         with torch.cuda.device(dev):
             st = _cabi.stream_ptr()
-
-            def edge_bwd(lo, n, gp):
-                ws_bytes = lib.hgn_edge_update_backward_workspace_bytes(BF, n)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                _cabi.check(lib.hgn_edge_update_backward(
-                    BF, n, e[lo:].data_ptr(), ps.data_ptr(), pr.data_ptr(), s32[lo:].data_ptr(), r32[lo:].data_ptr(), None, None,
-                    ctx.packed.data_ptr(), grad_out[lo:].data_ptr() if grad_out is not None else None, _cabi.ptr(grad_agg),
-                    grad_e[lo:].data_ptr(), g0[lo:].data_ptr(), *[g.data_ptr() for g in gp], ws.data_ptr(), ws_bytes, st),
-                    "hgn_edge_update_backward")
-
-            def project_bwd(n, v, gs, gr, grad_v, gw0):
-                ws_bytes = lib.hgn_edge_project_backward_workspace_bytes(BF, n)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                _cabi.check(lib.hgn_edge_project_backward(BF, n, v.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(),
-                                                          grad_v.data_ptr(), gw0.data_ptr(), ws.data_ptr(), ws_bytes, st),
-                            "hgn_edge_project_backward")
-
-            def seg_sum(data, n_rows, plan, n_seg, dst):
-                _cabi.check(lib.hgn_segment_reduce(BF, data.data_ptr(), n_rows, D, plan.perm.data_ptr(), plan.rowptr.data_ptr(), n_seg,
-                                                   dst.data_ptr(), None, None, None, None, None, 0, st), "hgn_segment_reduce")
-
-            gp = new_gparams()
-            back, works = None, []
-            if E - Ei:                                      # 1. cut edges first: their G0 rows hold everything the ghosts' gradient needs
-                edge_bwd(Ei, E - Ei, gp)
-                gs_cut = torch.empty((No + G, D), dtype=e.dtype, device=dev)
-                seg_sum(g0[Ei:], E - Ei, op.cut_plan, No + G, gs_cut)
-                grad_ghosts = torch.empty((G, D), dtype=e.dtype, device=dev)
-                gw0_ghost = torch.zeros(ctx.param_shapes[0], dtype=torch.float32, device=dev)
-                project_bwd(G, ghosts, gs_cut[No:], torch.zeros((G, D), dtype=e.dtype, device=dev), grad_ghosts, gw0_ghost)
-                back, works = _exchange_async(grad_ghosts, halo.ghost_splits, halo.send_splits, halo.group)   # 2. ghost gradients go home
-                gp[0] += gw0_ghost
-            if Ei:                                          # 3. interior edges while they travel
-                gp_int = new_gparams()
-                edge_bwd(0, Ei, gp_int)
-                for a, b in zip(gp, gp_int):
-                    a += b
-            gs = torch.empty((No + G, D), dtype=e.dtype, device=dev)           # 4. owned rows: sender- and receiver-keyed sums of ALL local G0 rows
-            gr = torch.empty((No, D), dtype=e.dtype, device=dev)
-            seg_sum(g0, E, op.s_plan, No + G, gs)
-            seg_sum(g0, E, op.r_plan, No, gr)
-            grad_owned = torch.empty((No, D), dtype=e.dtype, device=dev)
-            gw0_owned = torch.zeros(ctx.param_shapes[0], dtype=torch.float32, device=dev)
-            project_bwd(No, owned, gs, gr, grad_owned, gw0_owned)
-            gp[0] += gw0_owned
-            for w in works:                                 # 5. received ghost gradients are added at their owners, peers in rank order
-                w.wait()
-            if back is not None:
-                for q in range(len(halo.send_splits)):
-                    lo, hi = halo.peer_offsets[q], halo.peer_offsets[q + 1]
-                    if hi > lo:
-                        _scatter_add_rows(grad_owned, back[lo:hi], halo.send_index[lo:hi], halo.send_index32[lo:hi])
+            ws_bytes = lib.hgn_edge_update_backward_workspace_bytes(BF, E)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.hgn_edge_update_backward(
+                BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(), ctx.packed.data_ptr(),
+                _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(), *[g.data_ptr() for g in gp], ws.data_ptr(),
+                ws_bytes, st), "hgn_edge_update_backward")
+            for plan, n_seg, dst in ((s_plan, No + G, gs), (r_plan, No, gr)):
+                _cabi.check(lib.hgn_segment_reduce(BF, g0.data_ptr(), E, D, plan.perm.data_ptr(), plan.rowptr.data_ptr(), n_seg, dst.data_ptr(),
+                                                   None, None, None, None, None, 0, st), "hgn_segment_reduce")
+            halo.push_backward(step, layer, gs)              # ghost rows of gs go home; the rows of this rank's boundary nodes arrive
+            inbox = halo.inbox(layer)
+            lo = 0
+            for q in range(halo.world):                      # peers in rank order: a fixed summation order
+                n = halo.lg.send_splits[q]
+                if n and q != halo.rank:
+                    _cabi.check(lib.hgn_rows_scatter(BF, inbox[lo:lo + n].data_ptr(), halo.send_index32[lo:lo + n].data_ptr(), n, D, gs.data_ptr(), 1, st),
+                                "hgn_rows_scatter")
+                lo += n
+            pws_bytes = lib.hgn_edge_project_backward_workspace_bytes(BF, No)
+            pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.hgn_edge_project_backward(BF, No, owned.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(),
+                                                      grad_owned.data_ptr(), gp[0].data_ptr(), pws.data_ptr(), pws_bytes, st),
+                        "hgn_edge_project_backward")
         from . import ops as _ops
-        _ops._count(16)
-        return (grad_owned, grad_e, *gp, None, None)
+        _ops._count(12)
+        return (grad_owned, grad_e, *gp, None, None, None, None)
 
 
 class PartitionedProcessor(torch.nn.Module):
-    """Runs a (reference-API) ``Processor`` on one rank's share of the graph: ghosts are refreshed before
-    every block; the block itself is unchanged (it sees ``[owned | ghosts]`` as ``[mesh | hyper]`` rows).
+    """Runs a (reference-API) ``Processor`` on one rank's share of the graph.
 
-    With an ``OverlapPlan`` (edges listed interior-first), bf16 latents, plain ``GraphNet`` blocks, the 'sum' aggregator and one
-    edge set, ``HGN_HALO_OVERLAP=1`` makes every block run ``_PartitionedEdgeUpdate`` -- the halo exchange travels behind the
-    interior edge tiles -- followed by the projected node update on the owned rows.  Opt-in: it is validated against the generic
-    path (scripts/check_overlap.py, 2 GPUs) but measured SLOWER at N = 8 (28.4 vs 21.2 ms per step): the persistent edge kernels
-    occupy every SM, so the NCCL send/recv kernels get no SM until a compute CTA retires and each side ends up waiting for the
-    other; it needs compute grids that leave SMs to the communication kernels."""
+    Generic path (any block type, any aggregator, fp32 or bf16): ghosts are refreshed before every block with a grouped NCCL
+    send/recv; the block itself is unchanged (it sees ``[owned | ghosts]`` as ``[mesh | hyper]`` rows).
+    Fast path (``PeerHalo`` given; bf16, plain ``GraphNet`` blocks, 'sum', one edge set -- the cfg5 benchmark): ``_PeerEdgeUpdate``
+    per block -- halo rows travel as peer-memory stores issued by a kernel of the sending rank -- then the projected node update."""
 
-    def __init__(self, processor: torch.nn.Module, plan: HaloPlan, overlap: Optional[OverlapPlan] = None):
+    def __init__(self, processor: torch.nn.Module, plan: HaloPlan, peer: Optional[PeerHalo] = None):
         super().__init__()
         self.processor = processor
         self.plan = plan
-        self.overlap = overlap
+        self.peer = peer
+        if peer is not None:
+            from .plan import segment_plan
+            lg, dev = peer.lg, peer.device
+            peer.senders, peer.receivers = lg.senders.to(dev), lg.receivers.to(dev)
+            peer.s_plan = segment_plan(peer.senders, lg.n_own + lg.n_ghost)
+            peer.r_plan = segment_plan(peer.receivers, lg.n_own)
 
-    def _can_overlap(self, owned, edge_sets) -> bool:
-        import os
+    def _fast_path(self, owned, edge_sets) -> bool:
         from .migration.graphnet import GraphNet
         blocks = self.processor.graphnet_blocks
-        return (self.overlap is not None and os.environ.get("HGN_HALO_OVERLAP", "0") == "1" and owned.is_cuda
-                and len(edge_sets) == 1 and all(type(b) is GraphNet and b.message_passing_aggregator == "sum"
-                                                and list(b.edge_models.keys()) == [edge_sets[0].name] for b in blocks))
+        return (self.peer is not None and owned.is_cuda and len(edge_sets) == 1 and len(blocks) == self.peer.layers
+                and all(type(b) is GraphNet and b.message_passing_aggregator == "sum"
+                        and list(b.edge_models.keys()) == [edge_sets[0].name] for b in blocks))
 
     def forward(self, owned: torch.Tensor, edge_sets):
+        from . import config
         from .util import MultiGraph
-        precision = getattr(self.processor, "precision", None)
+        precision = getattr(self.processor, "precision", None) or config.precision()
         in_dtype = owned.dtype
         if precision == "bf16":
             owned = owned.to(torch.bfloat16)
             edge_sets = [es._replace(features=es.features.to(torch.bfloat16)) for es in edge_sets]
-        if precision == "bf16" and self._can_overlap(owned, edge_sets):
+        if precision == "bf16" and self._fast_path(owned, edge_sets):
             from . import ops as _ops
             from .migration.graphnet import _mlp_parameters, _packed_cache
             es = edge_sets[0]
             e = es.features
-            for block in self.processor.graphnet_blocks:
+            step = self.peer.steps_done
+            self.peer.steps_done += 1
+            for layer, block in enumerate(self.processor.graphnet_blocks):
                 edge_model = block.edge_models[es.name]
                 ep = _mlp_parameters(edge_model, 3 * owned.shape[1], owned)
                 with torch.cuda.device(owned.device):
                     packed = _ops._pack_weights(_packed_cache(edge_model), torch.bfloat16, 3, ep)
-                e, agg = _PartitionedEdgeUpdate.apply(owned, e, *ep, packed, self.overlap)
+                e, agg = _PeerEdgeUpdate.apply(owned, e, *ep, packed, self.peer, step, layer)
                 np_ = _mlp_parameters(block.node_model_cross, 2 * owned.shape[1], owned)
                 owned = _ops.node_update(np_, _packed_cache(block.node_model_cross), owned, agg)
             return owned.to(in_dtype), [es._replace(features=e)]
@@ -484,14 +561,18 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
     proc = proc.to(dev)
     proc.precision = "bf16"
     plan = HaloPlan(lg, dev)
-    model = PartitionedProcessor(proc, plan, OverlapPlan(lg, plan, dev))
+    use_peer = os.environ.get("HGN_HALO", "peer") == "peer"          # "nccl": the generic path (grouped send/recv before every block)
+    peer = PeerHalo(lg, layers, dev) if use_peer else None
+    model = PartitionedProcessor(proc, plan, peer)
     params = list(proc.parameters())
     v_dev, e_dev = v0.to(dev), e0.to(dev)
     v_host, e_host = v0.pin_memory(), e0.pin_memory()
     s_loc, r_loc = lg.senders.to(dev), lg.receivers.to(dev)
     loss_host = torch.empty(1).pin_memory()
 
-    def step(v_in, e_in):
+    kept = {}
+
+    def step(v_in, e_in, keep=False):
         for p in params:
             p.grad = None
         v = v_in.requires_grad_(True)
@@ -500,6 +581,8 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
         loss = (out_v * coef).sum() + out_sets[0].features.sum() * 1e-3
         loss.backward()
         allreduce_gradients(proc)
+        if keep:
+            kept.update(out_v=out_v.detach(), grad_v=v.grad.detach())
         return loss
 
     def timed(fn, steps):
@@ -559,6 +642,37 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
     e2e_ms = timed(run_e2e, 1) / e2e_steps
     halo_rows = torch.tensor([float(lg.n_ghost)], device=dev)
     dist.all_reduce(halo_rows, op=dist.ReduceOp.MAX)
+    # partition_check: one more (untimed) partitioned step; rank 0 then runs the SAME step on the whole mesh on its one GPU and
+    # compares its owned rows (latents and their gradients) and the all-reduced weight gradients
+    step(v_dev.detach(), e_dev.detach(), keep=True)
+    part_grads = [p.grad.detach().clone() for p in params]
+    torch.cuda.synchronize()
+    dist.barrier()
+    check = None
+    if rank == 0:
+        gen = torch.Generator().manual_seed(0)
+        v_full = torch.randn(n, 128, generator=gen)
+        e_full = torch.randn(e_total, 128, generator=gen)
+        coef_full = torch.randn(n, 128, generator=gen).to(dev)
+        for p in params:
+            p.grad = None
+        vf = v_full.to(dev).requires_grad_(True)
+        ef = e_full.to(dev).requires_grad_(True)
+        from .util import MultiGraph
+        out = proc(MultiGraph([vf], [EdgeSet("mesh_edges", ef, senders.to(dev), receivers.to(dev))]))
+        ((out.node_features[0] * coef_full).sum() + out.edge_sets[0].features.sum() * 1e-3).backward()
+        own = lg.owned.to(dev)
+
+        def rel(a, b):
+            return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+        check = {"latents_owned_rows": rel(kept["out_v"], out.node_features[0].detach()[own]),
+                 "latent_gradients_owned_rows": rel(kept["grad_v"], vf.grad[own]),
+                 "weight_gradients_worst": max(rel(a, p.grad) for a, p in zip(part_grads, params)),
+                 "metric": "relative L2, partitioned vs the same bf16 step on one GPU (rank 0's owned rows; all-reduced weight gradients)"}
+        check["value"] = max(check["latents_owned_rows"], check["latent_gradients_owned_rows"], check["weight_gradients_worst"])
+        del vf, ef, out
+        torch.cuda.empty_cache()
+    dist.barrier()
     if rank == 0:
         value = e_total * layers / (ms_per_step * 1e-3)
         print(json.dumps({
@@ -567,16 +681,18 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
             "data": "synthetic (seeded 1000x1000 triangulated grid, seeded weights)",
             "config": {"workload": "cfg5: 1M-node / 5 992 002-edge triangulated mesh, 15 GraphNet layers, sum aggregator, processor fwd+bwd",
                        "nodes": n, "edges": e_total, "layers": layers, "latent": 128,
-                       "partitioning": f"edge-cut, {world} row slabs, receiver-owner rule, halo of sender latents per layer "
-                                       f"(max {int(halo_rows)} ghost rows per rank), NCCL grouped send/recv "
-                                       f"{'overlapped with the interior edge tiles' if model._can_overlap(v_dev.to(torch.bfloat16), [EdgeSet('mesh_edges', e_dev, s_loc, r_loc)]) else 'before each block'}, "
-                                       "weight-gradient all-reduce",
+                       "partitioning": f"edge-cut, {world} row slabs, receiver-owner rule, one-ring halo per layer (max {int(halo_rows)} ghost "
+                                       f"rows per rank): " + ("rows of the sender table Ps pushed into the peers' tables over NVLink peer memory by a "
+                                       "kernel of the sending rank + flags (csrc/peer.cu), ghost gradients return the same way" if use_peer else
+                                       "node latents by NCCL grouped send/recv before each block") + ", weight-gradient all-reduce (NCCL)",
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": e_total * layers / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int((v_host.numel() + e_host.numel()) * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": roofline, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None, "partition_check": check,
             "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
             "kernel_times": "second pass of the same steps with the library's per-launch CUDA events enabled",
         }))
+    if peer is not None:
+        peer.close()
     dist.destroy_process_group()

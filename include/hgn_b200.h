@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HGN_B200_ABI_VERSION 4
+#define HGN_B200_ABI_VERSION 5
 
 typedef enum {
   HGN_OK = 0,
@@ -208,6 +208,33 @@ int hgn_colsum(int dtype, const void* x, int64_t rows, int32_t D, float* out,
 int hgn_rows_gather(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst, void* stream);
 int hgn_rows_scatter(int dtype, const void* src, const int32_t* idx, int64_t n, int32_t D, void* dst,
                      int accumulate, void* stream);
+
+/* ---- halo exchange over NVLink peer memory (one process per GPU) ----------------------------------------------------
+ * hgn_peer_alloc: cudaMalloc'ed, zero-filled exchange pool of this rank + its 64-byte CUDA IPC handle (send it to the peers,
+ * e.g. with torch.distributed.all_gather); hgn_peer_open maps a peer's pool into this process (peer access over NVLink is enabled
+ * lazily); _close / _free undo them.
+ * hgn_halo_push: for every peer q, rows send_index[row_begin[q] .. row_begin[q+1]) of `table` ([*, D]) are stored into dst[q]
+ * (a pointer INTO the peer's mapped pool: where its ghost rows / gradient inbox for this rank start), then flag[q] (a uint32 in
+ * the peer's pool) is set to `epoch` -- after all rows of all peers have been written and fenced.  `counter` is a zero-initialised
+ * uint32 in this rank's memory used by the kernel to find its last CTA (re-armed by the kernel).
+ * hgn_halo_wait: makes `stream` wait until every flag[q] (uint32s in THIS rank's pool, written by the peers) has reached `epoch`
+ * (wrap-safe comparison).  Epochs are the running number of the exchange, the same on all ranks; flags are never reset. */
+#define HGN_MAX_PEERS 16
+typedef struct {
+  void* dst[HGN_MAX_PEERS];
+  void* flag[HGN_MAX_PEERS];
+  int64_t row_begin[HGN_MAX_PEERS + 1];
+} hgn_halo_peers;
+typedef struct {
+  const void* flag[HGN_MAX_PEERS];
+} hgn_halo_flags;
+int hgn_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int hgn_peer_open(const unsigned char* handle64, void** ptr);
+int hgn_peer_close(void* ptr);
+int hgn_peer_free(void* ptr);
+int hgn_halo_push(int dtype, const void* table, const int32_t* send_index, int32_t D, const hgn_halo_peers* peers, int32_t n_peers,
+                  uint32_t epoch, void* counter, void* stream);
+int hgn_halo_wait(const hgn_halo_flags* flags, int32_t n_flags, uint32_t epoch, void* stream);
 
 /* ---- world edges: fixed-radius neighbour search ----------------------------------------------------
  * Replaces the dense search of PlateModel.build_graph (src/model/plate.py:86-110): torch.cdist over all

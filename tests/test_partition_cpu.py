@@ -75,7 +75,19 @@ def _oracle_block(weights, prefix, nodes, ghosts, es):
     return g.node_features[0], g.edge_sets[0]
 
 
+def _cpu_row_kernels():
+    """CPU stand-ins (torch indexing) for the two row kernels of the halo exchange: the product's ``_gather_rows`` /
+    ``_scatter_add_rows`` are CUDA only, these let the gloo runs exercise the exchange BOOKKEEPING without a GPU."""
+    partition._gather_rows = lambda src, index, index32: src.index_select(0, index)
+
+    def scatter_add(dst, rows, index, index32):
+        if rows.numel():
+            dst.index_add_(0, index, rows)
+    partition._scatter_add_rows = scatter_add
+
+
 def _worker(rank, world, port, tmpdir):
+    _cpu_row_kernels()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
