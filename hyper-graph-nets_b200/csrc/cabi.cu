@@ -86,7 +86,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
 // projected edge update (edge_tc.cu)
 int edge_project_forward_tc(int64_t num_nodes, const void* v, const void* packed, void* proj_s, void* proj_r, cudaStream_t st);
 size_t edge_project_backward_workspace_tc(int64_t num_nodes);
-int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
+int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, const void* grad_v_add, void* grad_v,
                              float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
                            const int32_t* receivers, const void* packed, void* out, cudaStream_t st);
@@ -207,13 +207,13 @@ extern "C" size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t n
 }
 
 extern "C" int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed, const void* grad_s,
-                                         const void* grad_r, void* grad_v, float* grad_W0, void* workspace, size_t workspace_bytes,
-                                         void* stream) {
+                                         const void* grad_r, const void* grad_v_add, void* grad_v, float* grad_W0, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
   HGN_BF16_ONLY("edge_project_backward");
   HGN_CHECK_ARG(num_nodes >= 0 && num_nodes < (int64_t(1) << 31), "edge_project_backward: num_nodes=%lld", (long long)num_nodes);
   HGN_CHECK_ARG(packed && grad_W0 && workspace, "edge_project_backward: null pointer");
   HGN_CHECK_ARG(num_nodes == 0 || (v && grad_s && grad_r && grad_v), "edge_project_backward: null pointer");
-  return edge_project_backward_tc(num_nodes, v, packed, grad_s, grad_r, grad_v, grad_W0, workspace, workspace_bytes,
+  return edge_project_backward_tc(num_nodes, v, packed, grad_s, grad_r, grad_v_add, grad_v, grad_W0, workspace, workspace_bytes,
                                   static_cast<cudaStream_t>(stream));
 }
 

@@ -41,6 +41,7 @@ constexpr int kLinThreads = kLinEpi + kLinProd + 32;
 struct LinArgs {
   const __nv_bfloat16* in[2];
   __nv_bfloat16* out[2];
+  const __nv_bfloat16* add;      // optional [rows,128]: added to out[0] in the epilogue (fp32), e.g. the node update's share of d loss / d v
   int n_in, n_out, b_mn, w0_chunks, chunk0;
 };
 
@@ -146,9 +147,19 @@ proj_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ pack
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32], w[16];
           tmem_ld32(tmem_base + lane_addr + s * 256 + o * 128 + cg * 32, v);
-          tmem_ld_wait();
+          if (la.add != nullptr && o == 0 && valid) {
+            ldg256(la.add + grow * kD + cg * 32, w); ldg256(la.add + grow * kD + cg * 32 + 16, w + 8);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            for (int j = 0; j < 16; ++j) {
+              const float2 x = unpack_bf16x2(w[j]);
+              w[j] = pack_bf16(__uint_as_float(v[2 * j]) + x.x, __uint_as_float(v[2 * j + 1]) + x.y);
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          }
           if (valid) { stg256(op + cg * 32, w); stg256(op + cg * 32 + 16, w + 8); }
         }
       }
@@ -799,13 +810,14 @@ size_t edge_project_backward_workspace_tc(int64_t num_nodes) {
   return size_t(tc_pair_wgrad_parts(num_nodes)) * 2 * kD * kD * sizeof(float) + 256;
 }
 
-int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, void* grad_v,
-                             float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packed, const void* grad_s, const void* grad_r, const void* grad_v_add,
+                             void* grad_v, float* grad_W0, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace_bytes < edge_project_backward_workspace_tc(num_nodes)) { set_error("edge_project_backward: workspace too small"); return HGN_ERR_WORKSPACE; }
   LinArgs la{};
   la.in[0] = static_cast<const __nv_bfloat16*>(grad_s);
   la.in[1] = static_cast<const __nv_bfloat16*>(grad_r);
   la.out[0] = static_cast<__nv_bfloat16*>(grad_v);
+  la.add = static_cast<const __nv_bfloat16*>(grad_v_add);
   la.n_in = 2; la.n_out = 1; la.b_mn = 1; la.w0_chunks = 3; la.chunk0 = 0;
   if (int rc = launch_proj(num_nodes, packed, la, "edge_project_dgrad", st)) return rc;
   float* partial = static_cast<float*>(workspace);

@@ -62,7 +62,7 @@ SIGNATURES = {
                          + [c_void_p] * 8 + [c_void_p, c_size_t, c_void_p]),
     "hgn_edge_project_forward": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hgn_edge_project_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
-    "hgn_edge_project_backward": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "hgn_edge_project_backward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p, c_size_t, c_void_p]),
     "hgn_edge_update_forward": (c_int, [c_int, c_int64] + [c_void_p] * 7 + [c_void_p]),
     "hgn_edge_update_backward_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hgn_edge_update_backward": (c_int, [c_int, c_int64] + [c_void_p] * 18 + [c_void_p, c_size_t, c_void_p]),

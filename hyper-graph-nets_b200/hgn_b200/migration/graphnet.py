@@ -154,8 +154,34 @@ class GraphNet(nn.Module):
         graph.node_features[0] = self._fused_node_update(graph, edge_sets, self.node_model_down, 0)
 
     # ---- schedules ---------------------------------------------------------------------------
+    def _whole_layer(self, graph: MultiGraph):
+        """The cfg5 shape -- plain GraphNet, 'sum', one edge set with a model, one node list, bf16 latents, at least one edge and
+        one node -- runs as a single autograd node (ops.graphnet_sum_layer): same kernels, no autograd glue between them."""
+        if (type(self) is not GraphNet or self.message_passing_aggregator != 'sum' or len(graph.node_features) != 1
+                or len(graph.edge_sets) != 1 or graph.edge_sets[0].name not in self.edge_models.keys()):
+            return None
+        v, es = graph.node_features[0], graph.edge_sets[0]
+        e = es.features
+        if (not v.is_cuda or v.dtype != torch.bfloat16 or e.dtype != torch.bfloat16 or v.shape[-1] != ops.D_LATENT
+                or e.shape[-1] != ops.D_LATENT or v.shape[0] == 0 or e.shape[0] == 0):
+            return None
+        edge_model = self.edge_models[es.name]
+        num_nodes = v.shape[0]
+        senders = segment_plan(to_device_index(es.senders, v.device), num_nodes)
+        receivers = segment_plan(to_device_index(es.receivers, v.device), num_nodes)
+        ep = _mlp_parameters(edge_model, 3 * v.shape[1], v)
+        np_ = _mlp_parameters(self.node_model_cross, 2 * v.shape[1], v)
+        v_new, e_new = ops.graphnet_sum_layer(ep, _packed_cache(edge_model), np_, _packed_cache(self.node_model_cross), v, e.to(v.device),
+                                              senders, receivers)
+        graph = graph._replace(edge_sets=[es._replace(features=e_new)])
+        graph.node_features[0] = v_new
+        return graph
+
     def forward(self, graph: MultiGraph, mask=None) -> MultiGraph:
         """graphnet.py:72-84: every edge set from the OLD node latents, then one mesh-node update."""
+        fused = self._whole_layer(graph)
+        if fused is not None:
+            return fused
         updated = [edge_set._replace(features=self._update_edge_features(graph.node_features, edge_set))
                    for edge_set in graph.edge_sets]
         graph = graph._replace(edge_sets=updated)

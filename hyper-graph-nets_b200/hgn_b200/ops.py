@@ -320,7 +320,7 @@ class _NodeProjection(torch.autograd.Function):
         with torch.cuda.device(v.device):
             ws_bytes = lib.hgn_edge_project_backward_workspace_bytes(_cabi.HGN_BF16, n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
-            _cabi.check(lib.hgn_edge_project_backward(_cabi.HGN_BF16, n, v.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(),
+            _cabi.check(lib.hgn_edge_project_backward(_cabi.HGN_BF16, n, v.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(), None,
                                                       grad_v.data_ptr(), grad_w0.data_ptr(), ws.data_ptr(), ws_bytes, _cabi.stream_ptr()),
                         "hgn_edge_project_backward")
         _count(4)
@@ -476,6 +476,91 @@ def node_update(params: Sequence[torch.Tensor], packed_cache: dict, v: torch.Ten
     with torch.cuda.device(v.device):
         packed = _pack_weights(packed_cache, torch.bfloat16, 1 + k, params)
     return _NodeUpdate.apply(v, *params, packed, *aggs)
+
+
+class _GraphNetSumLayer(torch.autograd.Function):
+    """One whole ``GraphNet`` block with the 'sum' aggregator and ONE edge set (graphnet.py:72-84) as a single autograd node:
+
+        forward   node projection -> fused edge update -> receiver aggregate -> aggregate projection + fused node update
+        backward  fused node backward -> fused edge backward (aggregate gradient gathered inside) -> sender / receiver sums of G0 ->
+                  node-level dgrad with the node update's share of d loss / d v added in its epilogue -> node-level wgrads
+
+    Same kernels and same arithmetic as ``edge_update`` + ``node_update``; what goes away is the autograd glue between them: the
+    ``at::add`` of the two partial gradients of ``v`` ([N,128] read twice and written once per layer), zero fills, and four autograd
+    nodes' worth of Python per layer."""
+
+    @staticmethod
+    def forward(ctx, v, e, s_plan, r_plan, packed_e, packed_n, *params):
+        lib, BF = _cabi.load(), _cabi.HGN_BF16
+        n, E = v.shape[0], e.shape[0]
+        ps, pr, q1 = torch.empty_like(v), torch.empty_like(v), torch.empty_like(v)
+        e_new, v_new, agg = torch.empty_like(e), torch.empty_like(v), torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            st = _cabi.stream_ptr()
+            _cabi.check(lib.hgn_edge_project_forward(BF, n, v.data_ptr(), packed_e.data_ptr(), ps.data_ptr(), pr.data_ptr(), st), "hgn_edge_project_forward")
+            _cabi.check(lib.hgn_edge_update_forward(BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
+                                                    packed_e.data_ptr(), e_new.data_ptr(), st), "hgn_edge_update_forward")
+            _cabi.check(lib.hgn_segment_reduce(BF, e_new.data_ptr(), E, D_LATENT, r_plan.perm.data_ptr(), r_plan.rowptr.data_ptr(), n, agg.data_ptr(),
+                                               None, None, None, None, None, 0, st), "hgn_segment_reduce")
+            agg_ptrs = (ctypes.c_void_p * 1)(agg.data_ptr())
+            _cabi.check(lib.hgn_node_update_forward(BF, n, v.data_ptr(), 1, agg_ptrs, packed_n.data_ptr(), q1.data_ptr(), None, v_new.data_ptr(), st),
+                        "hgn_node_update_forward")
+        _count(5)
+        ctx.save_for_backward(v, e, ps, pr, agg, q1)
+        ctx.plans, ctx.packed = (s_plan, r_plan), (packed_e, packed_n)
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        return v_new, e_new
+
+    @staticmethod
+    def backward(ctx, grad_v_new, grad_e_new):
+        lib, BF = _cabi.load(), _cabi.HGN_BF16
+        v, e, ps, pr, agg, q1 = ctx.saved_tensors
+        s_plan, r_plan = ctx.plans
+        packed_e, packed_n = ctx.packed
+        n, E, dev = v.shape[0], e.shape[0], v.device
+        grad_v_new = grad_v_new.contiguous().to(v.dtype) if grad_v_new is not None else torch.zeros_like(v)
+        grad_e_new = grad_e_new.contiguous().to(e.dtype) if grad_e_new is not None else None
+        new = lambda like: torch.empty_like(like)
+        grad_v_node, grad_agg, grad_v, gs, gr = new(v), new(v), new(v), new(v), new(v)
+        grad_e, g0 = new(e), new(e)
+        ge = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes[:8]]
+        gn = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ctx.param_shapes[8:]]
+        with torch.cuda.device(dev):
+            st = _cabi.stream_ptr()
+            agg_ptrs = (ctypes.c_void_p * 1)(agg.data_ptr())
+            gagg_ptrs = (ctypes.c_void_p * 1)(grad_agg.data_ptr())
+            ws_bytes = max(lib.hgn_node_update_backward_workspace_bytes(BF, n), lib.hgn_edge_update_backward_workspace_bytes(BF, E),
+                           lib.hgn_edge_project_backward_workspace_bytes(BF, n))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.hgn_node_update_backward(BF, n, v.data_ptr(), 1, agg_ptrs, q1.data_ptr(), None, packed_n.data_ptr(), grad_v_new.data_ptr(),
+                                                     grad_v_node.data_ptr(), gagg_ptrs, *[g.data_ptr() for g in gn], ws.data_ptr(), ws_bytes, st),
+                        "hgn_node_update_backward")
+            _cabi.check(lib.hgn_edge_update_backward(BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
+                                                     packed_e.data_ptr(), _cabi.ptr(grad_e_new), grad_agg.data_ptr(), grad_e.data_ptr(), g0.data_ptr(),
+                                                     *[g.data_ptr() for g in ge], ws.data_ptr(), ws_bytes, st), "hgn_edge_update_backward")
+            for plan, dst in ((s_plan, gs), (r_plan, gr)):
+                _cabi.check(lib.hgn_segment_reduce(BF, g0.data_ptr(), E, D_LATENT, plan.perm.data_ptr(), plan.rowptr.data_ptr(), n, dst.data_ptr(),
+                                                   None, None, None, None, None, 0, st), "hgn_segment_reduce")
+            # the edge backward wrote only the We block of d W0 (columns 256:384); the node-level kernel fills columns 0:256
+            _cabi.check(lib.hgn_edge_project_backward(BF, n, v.data_ptr(), packed_e.data_ptr(), gs.data_ptr(), gr.data_ptr(), grad_v_node.data_ptr(),
+                                                      grad_v.data_ptr(), ge[0].data_ptr(), ws.data_ptr(), ws_bytes, st), "hgn_edge_project_backward")
+        _count(5 + 2 + 2 + 4)
+        return (grad_v, grad_e, None, None, None, None, *ge, *gn)
+
+
+def graphnet_sum_layer(edge_params: Sequence[torch.Tensor], edge_cache: dict, node_params: Sequence[torch.Tensor], node_cache: dict,
+                       v: torch.Tensor, e: torch.Tensor, s_plan: SegmentPlan, r_plan: SegmentPlan):
+    """``(v', e')`` of one GraphNet block ('sum', one edge set, bf16 latents of width 128): see ``_GraphNetSumLayer``."""
+    _cabi.require_cuda(v, e)
+    if v.dtype != torch.bfloat16 or e.dtype != torch.bfloat16 or v.shape[-1] != D_LATENT or e.shape[-1] != D_LATENT:
+        raise _cabi.HgnError("graphnet_sum_layer is the bf16 tcgen05 path for latent 128")
+    if edge_params[0].shape != (D_LATENT, 3 * D_LATENT) or node_params[0].shape != (D_LATENT, 2 * D_LATENT):
+        raise _cabi.HgnError(f"graphnet_sum_layer: first linears {tuple(edge_params[0].shape)} / {tuple(node_params[0].shape)}")
+    v, e = v.contiguous(), e.contiguous()
+    with torch.cuda.device(v.device):
+        packed_e = _pack_weights(edge_cache, torch.bfloat16, 3, edge_params)
+        packed_n = _pack_weights(node_cache, torch.bfloat16, 2, node_params)
+    return _GraphNetSumLayer.apply(v, e, s_plan, r_plan, packed_e, packed_n, *edge_params, *node_params)
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:

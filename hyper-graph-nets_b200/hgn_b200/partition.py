@@ -424,7 +424,7 @@ class _PeerEdgeUpdate(torch.autograd.Function):
                 lo += n
             pws_bytes = lib.hgn_edge_project_backward_workspace_bytes(BF, No)
             pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
-            _cabi.check(lib.hgn_edge_project_backward(BF, No, owned.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(),
+            _cabi.check(lib.hgn_edge_project_backward(BF, No, owned.data_ptr(), ctx.packed.data_ptr(), gs.data_ptr(), gr.data_ptr(), None,
                                                       grad_owned.data_ptr(), gp[0].data_ptr(), pws.data_ptr(), pws_bytes, st),
                         "hgn_edge_project_backward")
         from . import ops as _ops
@@ -565,8 +565,8 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
     peer = PeerHalo(lg, layers, dev) if use_peer else None
     model = PartitionedProcessor(proc, plan, peer)
     params = list(proc.parameters())
-    v_dev, e_dev = v0.to(dev), e0.to(dev)
-    v_host, e_host = v0.pin_memory(), e0.pin_memory()
+    v_dev, e_dev = v0.to(dev).to(torch.bfloat16), e0.to(dev).to(torch.bfloat16)     # resident: the dtype the path computes in
+    v_host, e_host = v0.pin_memory(), e0.pin_memory()                                # e2e: fp32 host buffers
     s_loc, r_loc = lg.senders.to(dev), lg.receivers.to(dev)
     loss_host = torch.empty(1).pin_memory()
 

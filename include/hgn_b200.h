@@ -152,11 +152,13 @@ int hgn_mlp_backward(int dtype, int64_t rows, const hgn_chunks* chunks, const vo
  * `packed` is the hgn_mlp_pack blob of the edge MLP with n_chunks = 3.  senders/receivers: int32 [E]. */
 int hgn_edge_project_forward(int dtype, int64_t num_nodes, const void* v, const void* packed,
                              void* proj_s, void* proj_r, void* stream);
-/* grad_v[N,128] = grad_s Ws + grad_r Wr ; grad_W0[128,384] columns 0:256 = [grad_s^T v | grad_r^T v] (columns
- * 256:384 are left untouched), where grad_s / grad_r are the sender- / receiver-keyed segment sums of grad_pre0. */
+/* grad_v[N,128] = grad_s Ws + grad_r Wr (+ grad_v_add when not NULL: the other consumers' share of d loss / d v, e.g. the node
+ * update's, added in the kernel's epilogue instead of by a separate pass); grad_W0[128,384] columns 0:256 =
+ * [grad_s^T v | grad_r^T v] (columns 256:384 are left untouched), where grad_s / grad_r are the sender- / receiver-keyed segment
+ * sums of grad_pre0. */
 size_t hgn_edge_project_backward_workspace_bytes(int dtype, int64_t num_nodes);
 int hgn_edge_project_backward(int dtype, int64_t num_nodes, const void* v, const void* packed,
-                              const void* grad_s, const void* grad_r, void* grad_v, float* grad_W0,
+                              const void* grad_s, const void* grad_r, const void* grad_v_add, void* grad_v, float* grad_W0,
                               void* workspace, size_t workspace_bytes, void* stream);
 int hgn_edge_update_forward(int dtype, int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r,
                             const int32_t* senders, const int32_t* receivers, const void* packed, void* out, void* stream);
