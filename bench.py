@@ -147,6 +147,109 @@ def make_processor(weights, layers, precision, device, aggregator="sum"):
     return proc
 
 
+def fp32_parity_mode(dev):
+    """The 1e-5 parity mode (`precision = "fp32"`: fp32 storage, FFMA kernels) beside the bf16 headline, against an fp32 denominator
+    measured here the way MEASURED_PEAKS.json measures bf16: torch.matmul fp32 8192^3 with TF32 off, best of 10 and a
+    1.5 s back-to-back loop; then the processor on a 1000 x 250 slab of the cfg5 mesh, 3 layers, fwd+bwd.  Not a roofline target."""
+    from hgn_b200.util import EdgeSet, MultiGraph
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(10):
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); a @ b; t1.record(); torch.cuda.synchronize()
+            best = max(best, 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, wall = 0, time.perf_counter()
+        t0.record()
+        while time.perf_counter() - wall < 1.5:
+            for _ in range(10):
+                a @ b
+            reps += 10
+            torch.cuda.synchronize()
+        t1.record(); torch.cuda.synchronize()
+        sustained = reps * 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
+        del a, b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    W, H, L = 1000, 250, 3
+    data = build_inputs(W, H, L)
+    proc = make_processor(data["weights"], L, "fp32", dev)
+    params = list(proc.parameters())
+    s_, r_ = data["senders"].to(dev), data["receivers"].to(dev)
+    v0, e0, coef = data["v0"].to(dev), data["e0"].to(dev), data["coef_v"].to(dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        v, ed = v0.detach().requires_grad_(True), e0.detach().requires_grad_(True)
+        out = proc(MultiGraph([v], [EdgeSet("mesh_edges", ed, s_, r_)]))
+        ((out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3).backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        step()
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 3
+    flops = 3 * (data["e"] * F_EDGE + data["n"] * F_NODE_SUM) * L
+    return {"edge_updates_per_s": data["e"] * L / (ms * 1e-3), "ms_per_step": ms, "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "fp32_matmul_tflops_sustained": sustained, "fp32_matmul_tflops_best": best, "frac": flops / (ms * 1e-3) / 1e12 / sustained,
+            "mesh": f"{W}x{H} slab of the cfg5 mesh ({data['n']} nodes, {data['e']} directed edges), {L} layers, sum, fwd+bwd",
+            "what": "precision = 'fp32': the 1e-5 parity mode (FFMA kernels), not a roofline target; peak = torch.matmul fp32, TF32 off, measured in this run"}
+
+
+def data_parallel_cfg4_leg(world, rank, dev, steps=20):
+    """BASELINE.json configs[3] beside the partitioned cfg5 line of an N > 1 run: cylinder_flow-shaped batches (48x40 mesh x 21,
+    GraphNet pna, 5 layers, bf16), every rank a replica with its own batch (seed = rank), one flat fp32 gradient all-reduce per step
+    (partition.allreduce_gradients) -- trajectory data parallelism, weak scaling.  Returns the JSON sub-object (rank 0) or None."""
+    import torch.distributed as dist
+    from hgn_b200 import partition
+    from hgn_b200.util import EdgeSet, MultiGraph
+    gw, gh, batch, layers, agg, _, wl_text = WORKLOADS["cfg4"]
+    data = build_inputs(gw, gh, layers, seed=rank, aggregator=agg, batch=batch)
+    proc = make_processor(data["weights"], layers, "bf16", dev, agg)
+    params = list(proc.parameters())
+    senders, receivers = data["senders"].to(dev), data["receivers"].to(dev)
+    v_dev, e_dev, coef = data["v0"].to(dev).to(torch.bfloat16), data["e0"].to(dev).to(torch.bfloat16), data["coef_v"].to(dev)
+
+    def step():
+        for p in params:
+            p.grad = None
+        v, ed = v_dev.detach().requires_grad_(True), e_dev.detach().requires_grad_(True)
+        out = proc(MultiGraph([v], [EdgeSet("mesh_edges", ed, senders, receivers)]))
+        ((out.node_features[0] * coef).sum() + out.edge_sets[0].features.sum() * 1e-3).backward()
+        partition.allreduce_gradients(proc)
+
+    for _ in range(5):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms = float(ms)
+    return {"value": data["e"] * layers * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "scaling": "weak",
+            "workload": f"{wl_text}, {layers} GraphNet layers, {agg}, processor fwd+bwd + gradient all-reduce; one batch per rank",
+            "edges_per_rank": data["e"]}
+
+
 def run_ours(args):
     from hgn_b200 import _cabi, ops, partition
     from hgn_b200.util import EdgeSet, MultiGraph
@@ -162,7 +265,7 @@ def run_ours(args):
         from hgn_b200 import partition
         args.aggregator = args.aggregator or "sum"
         return partition.bench_partitioned(args, world, rank, dev, GRID_W, GRID_H, LAYERS, METRIC, UNIT, load_peaks(), ClockSampler,
-                                           dominant_kernel_roofline)
+                                           dominant_kernel_roofline, extra_leg=data_parallel_cfg4_leg)
 
     gw, gh, batch, layers, default_agg, cpu_sample, wl_text = WORKLOADS[args.workload]
     args.aggregator = args.aggregator or default_agg
@@ -315,6 +418,9 @@ def run_ours(args):
         del proc, params, v_dev, e_dev
         torch.cuda.empty_cache()
         line["torch_cuda_reference"] = torch_cuda_reference(dev, data, args.aggregator, layers if args.workload != "cfg5" else 1)
+        if args.workload == "cfg5":
+            torch.cuda.empty_cache()
+            line["fp32_parity_mode"] = fp32_parity_mode(dev)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -504,6 +610,16 @@ def graphed_step(step_fn, params, steps, edge_updates_per_step):
         return {"value": None, "error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
+def ncu_traffic(kernel_name):
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            entry = json.load(f).get("kernels", {}).get(kernel_name)
+        return float(entry["dram_bytes_per_launch"]) if entry else None
+    except (OSError, ValueError, KeyError, TypeError):
+        return None
+
+
 def dominant_kernel_roofline(kernels, steps, e, n, peaks):
     """Algorithmic FLOPs per launch (GEMM flops of the reference's arithmetic, backward = 2x forward,
     recompute earns no credit) over the mean launch time of the kernel that takes the most time in the step.
@@ -520,10 +636,10 @@ def dominant_kernel_roofline(kernels, steps, e, n, peaks):
         "mlp_tile_tc_fwd": (n, F_NODE_SUM, F_NODE_SUM), "mlp_tile_tc_bwd": (n, F_NODE_SUM, 2 * F_NODE_SUM),
         "mlp_wgrad_tc": (n, F_NODE_SUM, F_NODE_SUM),
     }.get(top["name"])
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch at the full cfg5 size, from the ncu --set full capture in
-    # profiles/r1_final_ncu_full_edge_kernels.txt (only meaningful for the single-GPU cfg5 launch sizes)
-    ncu_traffic = {"edge_bwd_tc": 4.699e9 + 3.050e9, "edge_fwd_tc": 2.609e9 + 1.501e9, "segment_reduce": 1.562e9 + 0.247e9}
-    traffic = ncu_traffic.get(top["name"]) if e == 5992002 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at the full cfg5 size: read from profiles/ncu_traffic.json, which
+    # scripts/ncu_summary.py --json writes from an `ncu --set full` capture (kernel, bytes, source report, commit); null when that
+    # file has no entry for the kernel or the launch is not the cfg5 size
+    traffic = ncu_traffic(top["name"]) if e == 5992002 else None
     if tensor is not None:
         rows, algo_row, exec_row = tensor
         achieved = rows * algo_row / (mean_ms * 1e-3) / 1e12
@@ -639,9 +755,67 @@ def rollout_bench(dev):
             out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
     finally:
         hgn_b200.set_precision(prev_precision)
-    ref = _reference_subprocess(["--steps", "1", "--warmup", "1", "--rollout-steps", "10"], timeout=900)
+    ref = _reference_subprocess(["--steps", "1", "--warmup", "1", "--rollout-steps", "10", "--train-steps", "5"], timeout=900)
     if ref is not None and ref.get("rollout"):
         out["cpu_reference"] = ref["rollout"]
+    try:
+        out["training"] = training_bench(FlagModel, dev, ref.get("training") if ref else None)
+    except Exception as exc:
+        out["training"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    return out
+
+
+TRAIN_STEPS = 100
+
+
+def flag_training_loop(model, frame, optimizer, steps):
+    """The reference's inner training loop on one frame (MeshSimulator.py:131-139)."""
+    for _ in range(steps):
+        graph = model.build_graph(frame, True)
+        loss = model.training_step(graph, frame)
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+    return loss
+
+
+def training_bench(FlagModel, dev, cpu_reference):
+    """Training iterations/s of the flag_simple-shaped model (BASELINE.json configs[1]: 1 600 nodes, GraphNet pna, 15 layers; one
+    frame per iteration): the reference's own loop (build_graph, FlagModel.training_step, backward, Adam) on the installed hgn_b200
+    modules in bf16, the same iteration captured in one CUDA graph (hgn_b200.graphed.FlagTrainingGraph), and the unmodified
+    reference on the host cores."""
+    import copy
+    import hgn_b200
+    from hgn_b200.graphed import FlagTrainingGraph
+    prev_precision = hgn_b200.precision()
+    hgn_b200.set_precision("bf16")
+    try:
+        model, traj = rollout_model_and_trajectory(FlagModel, dev, 2)
+        frame = {k: v[0] for k, v in traj.items()}
+        model.train()
+        twin = copy.deepcopy(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        flag_training_loop(model, frame, opt, 5)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = flag_training_loop(model, frame, opt, TRAIN_STEPS)
+        torch.cuda.synchronize()
+        out = {"unit": "training iterations/s", "steps": TRAIN_STEPS, "value": TRAIN_STEPS / (time.perf_counter() - t0), "via": "FlagModel.training_step + Adam",
+               "finite": bool(torch.isfinite(loss))}
+        runner = FlagTrainingGraph(twin, frame, torch.optim.Adam(twin.parameters(), lr=1e-4, capturable=True))
+        for _ in range(5):
+            runner.step(frame)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(TRAIN_STEPS):
+            loss = runner.step(frame)
+        torch.cuda.synchronize()
+        out["cuda_graph"] = {"value": TRAIN_STEPS / (time.perf_counter() - t0), "finite": bool(torch.isfinite(loss)),
+                             "what": "the same iteration (normalisers, encoder, 15 layers, decoder, masked loss, backward, Adam) as one CUDA graph"}
+    finally:
+        hgn_b200.set_precision(prev_precision)
+    if cpu_reference:
+        out["cpu_reference"] = cpu_reference
     return out
 
 
@@ -837,6 +1011,20 @@ def run_reference(args):
     if getattr(args, "rollout_steps", 0) > 0 and kind == "reference":
         line["rollout"] = {"value": reference_rollout(args.rollout_steps), "unit": "rollout steps/s", "steps": args.rollout_steps, "cores": cores,
                            "via": "FlagModel.rollout (unmodified reference, CPU)"}
+    if getattr(args, "train_steps", 0) > 0 and kind == "reference":
+        shim = _reference_shim()
+        shim.load()
+        os.chdir(shim.REFERENCE_ROOT)
+        from src.model.flag import FlagModel
+        model, traj = rollout_model_and_trajectory(FlagModel, torch.device("cpu"), 2)
+        frame = {k: v[0] for k, v in traj.items()}
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        flag_training_loop(model, frame, opt, 1)
+        t0 = time.perf_counter()
+        flag_training_loop(model, frame, opt, args.train_steps)
+        line["training"] = {"value": args.train_steps / (time.perf_counter() - t0), "unit": "training iterations/s", "steps": args.train_steps,
+                            "cores": cores, "via": "FlagModel.training_step + Adam (unmodified reference, CPU)"}
     print(json.dumps(line))
 
 
@@ -850,6 +1038,7 @@ def main():
                     help="message-passing aggregator (default: the workload's; the headline metric is quoted on 'sum'; 'pna' is the "
                          "reference configs' default)")
     ap.add_argument("--rollout-steps", type=int, default=0, help="reference arm only: also time FlagModel.rollout for this many steps")
+    ap.add_argument("--train-steps", type=int, default=0, help="reference arm only: also time this many FlagModel training iterations")
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + ["cfg3"],
                     help="cfg5 = the headline 1M/6M mesh (the bench line); cfg2 / cfg4 = small-mesh batched training shapes; "
                          "cfg3 = HeteroGraphNet on a plateCluster-shaped batch (single GPU)")

@@ -121,3 +121,77 @@ def flag_rollout_steps_per_second(model, traj, steps: int) -> dict:
     return {"value": steps / (time.perf_counter() - t0), "unit": "rollout steps/s", "steps": steps,
             "max_error_vs_FlagModel_rollout_relative_to_distance_travelled": err, "checked_steps": check_steps,
             "what": "FlagModel.rollout's step (same model object and normalisers) captured in one CUDA graph per step (hgn_b200.graphed.FlagRolloutGraph)"}
+
+
+class FlagTrainingGraph:
+    """One training iteration of the reference's loop for a flag-style model -- ``FlagModel.build_graph`` with its accumulating
+    normalisers, ``training_step`` (encoder, processor, decoder, target normalisation, MSE over the NORMAL nodes; flag.py:143-154),
+    ``loss.backward()`` and ``optimizer.step()`` (MeshSimulator.py:131-139) -- captured in ONE CUDA graph and replayed per frame.
+
+    Same model object, normalisers and optimizer as the eager loop; two things are restated so that nothing returns to the host:
+    the per-trajectory constants of ``build_graph`` are hoisted (``graph_building.FlagGraphBuilder``) and the masked loss
+    ``mse(target[mask], out[mask])`` is computed as ``sum(mask * (target - out)^2) / (3 * count(mask))`` (the same number; boolean
+    indexing has a data-dependent shape).  The optimizer must be capture-safe (``torch.optim.Adam(..., capturable=True)`` or SGD).
+    The warm-up iterations torch needs before a capture are undone: weights, optimizer state and normaliser statistics are restored
+    in place, so the first ``step`` is the first training iteration."""
+
+    def __init__(self, model, frame, optimizer, warmup: int = 3):
+        from .graph_building import FlagGraphBuilder
+        from .util import NodeType
+        _cabi.require_cuda(frame['world_pos'])
+        self.model, self.optimizer = model, optimizer
+        self.builder = FlagGraphBuilder(model, frame)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        mask = torch.eq(frame['node_type'][:, 0], int(NodeType.NORMAL))
+        self.maskf = mask.to(torch.float32).unsqueeze(1)
+        self.inv_count = 1.0 / (3.0 * float(mask.sum()))
+        self.inputs = {k: frame[k].clone() for k in ('world_pos', 'prev|world_pos', 'target|world_pos')}
+        self.loss = None
+
+        def step():
+            optimizer.zero_grad(set_to_none=True)
+            graph = self.builder(self.inputs, True, node_dynamic=False)
+            out = model(graph)
+            target = model.get_target(self.inputs, True)
+            diff = (target - out) * self.maskf
+            loss = (diff * diff).sum() * self.inv_count
+            loss.backward()
+            optimizer.step()
+            return loss.detach()
+
+        # everything the warm-up iterations change, restored IN PLACE after the capture (the graph holds these tensors' addresses)
+        with torch.no_grad():
+            model(self.builder(self.inputs, False, node_dynamic=False))          # lazy linears, plans, packed weights
+        saved_params = [p.detach().clone() for p in self.params]
+        normalizers = [m for m in model.modules() if hasattr(m, '_acc_sum') and hasattr(m, '_num_accumulations')]
+        fields = ('_acc_sum', '_acc_sum_squared', '_acc_count', '_num_accumulations')
+        saved_norm = [[getattr(nz, f).clone() for f in fields] for nz in normalizers]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        for p in self.params:
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step()
+        with torch.no_grad():
+            for p, w in zip(self.params, saved_params):
+                p.copy_(w)
+            for nz, vals in zip(normalizers, saved_norm):
+                for f, val in zip(fields, vals):
+                    getattr(nz, f).copy_(val)
+            for state in optimizer.state.values():
+                for key, val in state.items():
+                    if torch.is_tensor(val):
+                        val.zero_()
+
+    def step(self, frame) -> torch.Tensor:
+        """One training iteration on ``frame`` (same mesh as the one given at construction); returns the loss (a device scalar that
+        the next ``step`` overwrites)."""
+        for k, buf in self.inputs.items():
+            buf.copy_(frame[k])
+        self.graph.replay()
+        return self.loss

@@ -21,9 +21,17 @@ class Normalizer(nn.Module):
         self._acc_sum_squared = torch.zeros(size, dtype=torch.float32, device=dev)
 
     def forward(self, batched_data: Tensor, accumulate=True) -> Tensor:
-        """Normalizes input data and accumulates statistics (at most ``max_accumulations`` times)."""
-        if accumulate and self._num_accumulations < self._max_accumulations:
-            self._accumulate(batched_data)
+        """Normalizes input data and accumulates statistics (at most ``max_accumulations`` times).
+
+        While a CUDA graph is being captured (``hgn_b200.graphed``) the accumulation becomes part of the graph: it updates the
+        statistics IN PLACE -- every replay must add to what the previous replay left -- and the reference's host-side comparison
+        of the accumulation counter (a device read-back, normalizer.py:44) is not made: a captured step always accumulates (the
+        limit is 10^6 accumulations, about 50 000 trajectories)."""
+        if accumulate:
+            if batched_data.is_cuda and torch.cuda.is_current_stream_capturing():
+                self._accumulate_in_place(batched_data)
+            elif self._num_accumulations < self._max_accumulations:
+                self._accumulate(batched_data)
         return (batched_data - self._mean()) / self._std_with_epsilon()
 
     def inverse(self, normalized_batch_data: Tensor) -> Tensor:
@@ -35,6 +43,12 @@ class Normalizer(nn.Module):
         self._acc_sum_squared = self._acc_sum_squared.add(torch.sum(batched_data ** 2, dim=0))
         self._acc_count = self._acc_count.add(rows)
         self._num_accumulations = self._num_accumulations.add(1.)
+
+    def _accumulate_in_place(self, batched_data: Tensor) -> None:
+        self._acc_sum.add_(torch.sum(batched_data, dim=0))
+        self._acc_sum_squared.add_(torch.sum(batched_data ** 2, dim=0))
+        self._acc_count.add_(float(batched_data.shape[0]))
+        self._num_accumulations.add_(1.)
 
     def _safe_count(self) -> Tensor:
         return torch.maximum(self._acc_count, torch.ones_like(self._acc_count))

@@ -538,7 +538,7 @@ def allreduce_normalizers(normalizers, group=None) -> None:
 # ------------------------------------------------------------------------------------------------------
 # multi-GPU benchmark (bench.py --gpus N under torchrun)
 # ------------------------------------------------------------------------------------------------------
-def bench_partitioned(args, world, rank, dev, width, height, layers, metric, unit, peaks, clock_sampler_cls, roofline_fn=None):
+def bench_partitioned(args, world, rank, dev, width, height, layers, metric, unit, peaks, clock_sampler_cls, roofline_fn=None, extra_leg=None):
     import json
     import os
     from . import ops, synthetic
@@ -673,6 +673,7 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
         del vf, ef, out
         torch.cuda.empty_cache()
     dist.barrier()
+    extra = extra_leg(world, rank, dev) if extra_leg is not None else None      # e.g. the data-parallel cfg4 leg (all ranks take part)
     if rank == 0:
         value = e_total * layers / (ms_per_step * 1e-3)
         print(json.dumps({
@@ -689,7 +690,7 @@ def bench_partitioned(args, world, rank, dev, width, height, layers, metric, uni
             "e2e": {"value": e_total * layers / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int((v_host.numel() + e_host.numel()) * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": roofline, "cpu_baseline": None, "partition_check": check,
+            "roofline": roofline, "cpu_baseline": None, "partition_check": check, "data_parallel_cfg4": extra,
             "kernels": [{"name": k["name"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps} for k in kernels],
             "kernel_times": "second pass of the same steps with the library's per-launch CUDA events enabled",
         }))

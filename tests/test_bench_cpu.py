@@ -62,7 +62,8 @@ def test_roofline_accounting_of_the_projected_kernels():
     assert r["kernel"] == "edge_bwd_tc" and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
     assert abs(r["achieved"] - e * 20 * 128 * 128 / 3.5e-3 / 1e12) < 1e-6           # backward = 2 x 10 D^2 per edge
     assert abs(r["frac"] - r["achieved"] / 1378.8) < 1e-12 and r["executed_tflops"] < r["achieved"]
-    assert r["traffic"] == 4.699e9 + 3.050e9                                         # ncu capture, cfg5 launch size only
+    assert r["traffic"] == bench.ncu_traffic("edge_bwd_tc")                          # profiles/ncu_traffic.json (ncu capture), cfg5 launch size only
+    assert r["traffic"] is None or 4e9 < r["traffic"] < 2e10
     assert bench.dominant_kernel_roofline(kernels, 1, 1000, 100, peaks)["traffic"] is None
     seg = bench.dominant_kernel_roofline([{"name": "segment_reduce", "launches": 3, "ms": 0.93}], 1, e, n, peaks)
     assert seg["bound"] == "hbm" and abs(seg["achieved"] - ((e + n) * 256 + e * 4) / 0.31e-3 / 1e9) < 1e-6
