@@ -99,4 +99,29 @@ __device__ __forceinline__ float ordered_sum(const float* __restrict__ src, int 
   return (s0 + s1) + (s2 + s3);
 }
 
+
+// The same sum by a whole 256-thread block for 32 adjacent outputs: lane = output, warp g sums parts g, g + 8, g + 16 ... (a warp
+// reads 128 contiguous bytes per part), the eight warp sums are combined through shared memory as ((0+1)+(2+3))+((4+5)+(6+7)).
+// Fixed order, and eight times the loads in flight of the one-thread-per-output version (which took 31 us for the 148 per-CTA
+// partials of one edge backward -- a fixed cost per layer at every GPU count).  `src` may be null for an inactive lane; the
+// result is valid in warp 0 only.  `sm` = 256 floats.
+__device__ __forceinline__ float ordered_sum_block8(const float* __restrict__ src, int parts, int64_t stride, float* sm) {
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (src != nullptr) {
+    int p = g;
+    for (; p + 24 < parts; p += 32) {
+      const float x0 = __ldg(src + int64_t(p) * stride), x1 = __ldg(src + int64_t(p + 8) * stride);
+      const float x2 = __ldg(src + int64_t(p + 16) * stride), x3 = __ldg(src + int64_t(p + 24) * stride);
+      a0 += x0; a1 += x1; a2 += x2; a3 += x3;
+    }
+    if (p < parts) a0 += __ldg(src + int64_t(p) * stride);
+    if (p + 8 < parts) a1 += __ldg(src + int64_t(p + 8) * stride);
+    if (p + 16 < parts) a2 += __ldg(src + int64_t(p + 16) * stride);
+  }
+  sm[g * 32 + lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  return ((sm[lane] + sm[32 + lane]) + (sm[64 + lane] + sm[96 + lane])) + ((sm[128 + lane] + sm[160 + lane]) + (sm[192 + lane] + sm[224 + lane]));
+}
+
 }  // namespace hgn

@@ -147,18 +147,18 @@ proj_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ pack
         for (int cg = 0; cg < 4; ++cg) {
           uint32_t v[32], w[16];
           tmem_ld32(tmem_base + lane_addr + s * 256 + o * 128 + cg * 32, v);
-          if (la.add != nullptr && o == 0 && valid) {
-            ldg256(la.add + grow * kD + cg * 32, w); ldg256(la.add + grow * kD + cg * 32 + 16, w + 8);
-            tmem_ld_wait();
+          // tcgen05.ld / tcgen05.wait are .sync.aligned: every lane of the warp executes them together, so only the global loads
+          // are guarded by the per-lane `valid` (a tail tile of a small graph has valid and invalid rows inside one warp)
+          const bool add_row = la.add != nullptr && o == 0 && valid;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 x = unpack_bf16x2(w[j]);
-              w[j] = pack_bf16(__uint_as_float(v[2 * j]) + x.x, __uint_as_float(v[2 * j + 1]) + x.y);
-            }
-          } else {
-            tmem_ld_wait();
+          for (int j = 0; j < 16; ++j) w[j] = 0u;
+          if (add_row) { ldg256(la.add + grow * kD + cg * 32, w); ldg256(la.add + grow * kD + cg * 32 + 16, w + 8); }
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = unpack_bf16x2(w[j]);
+            w[j] = add_row ? pack_bf16(__uint_as_float(v[2 * j]) + x.x, __uint_as_float(v[2 * j + 1]) + x.y)
+                           : pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           }
           if (valid) { stg256(op + cg * 32, w); stg256(op + cg * 32 + 16, w + 8); }
         }
@@ -735,38 +735,48 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
 }
 
 // fixed-order reduction of the per-CTA partials of edge_bwd_tc_kernel
-__global__ void edge_bwd_reduce_kernel(const float* __restrict__ w_partial, const float* __restrict__ epi_colpart,
-                                       const float* __restrict__ prod_colpart, int parts, int w0_chunks, int w0_chunk0, int skip_we, float* __restrict__ gW0, float* __restrict__ gW1,
-                                       float* __restrict__ gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+edge_bwd_reduce_kernel(const float* __restrict__ w_partial, const float* __restrict__ epi_colpart,
+                       const float* __restrict__ prod_colpart, int parts, int w0_chunks, int w0_chunk0, int skip_we, float* __restrict__ gW0, float* __restrict__ gW1,
+                       float* __restrict__ gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta) {
+  __shared__ float sm[256];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);         // 32 outputs per block (common.cuh, ordered_sum_block8)
+  const float* src = nullptr;
+  int n = parts;
+  int64_t stride = 0;
   if (i < 3 * kD * kD) {
-    if (skip_we && i < kD * kD) return;          // dWe comes from the streaming weight-gradient kernel
-    const float s = ordered_sum(w_partial + i, parts, int64_t(3) * kD * kD);
+    if (!(skip_we && i < kD * kD)) { src = w_partial + i; stride = int64_t(3) * kD * kD; }    // dWe may come from the streaming weight-gradient kernel
+  } else if (i < 3 * kD * kD + 5 * kD) {
+    const int k = (i - 3 * kD * kD) / kD, c = i % kD;
+    if (k < 3) { src = prod_colpart + int64_t(k) * kD + c; stride = int64_t(3) * kD; }
+    else { src = epi_colpart + int64_t(k - 3) * kD + c; n = parts * 4; stride = int64_t(2) * kD; }
+  }
+  const float s = ordered_sum_block8(src, n, stride, sm);
+  if (threadIdx.x >= 32 || src == nullptr) return;
+  if (i < 3 * kD * kD) {
     const int z = i / (kD * kD), o = (i / kD) % kD, c = i % kD;
     if (z == 0) gW0[(int64_t(o) * w0_chunks + w0_chunk0) * kD + c] = s;
     else if (z == 1) gW1[o * kD + c] = s;
     else gW2[o * kD + c] = s;
-  } else if (i < 3 * kD * kD + 5 * kD) {
+  } else {
     const int k = (i - 3 * kD * kD) / kD, c = i % kD;
-    if (k < 3) {
-      (k == 0 ? gb2 : k == 1 ? gb1 : gb0)[c] = ordered_sum(prod_colpart + int64_t(k) * kD + c, parts, int64_t(3) * kD);
-    } else {
-      (k == 3 ? gbeta : ggamma)[c] = ordered_sum(epi_colpart + int64_t(k - 3) * kD + c, parts * 4, int64_t(2) * kD);
-    }
+    (k == 0 ? gb2 : k == 1 ? gb1 : k == 2 ? gb0 : k == 3 ? gbeta : ggamma)[c] = s;
   }
 }
 
 // gW0[:, col0 : col0+128] = sum_p partial[p][z]   (partials of the pair weight-gradient kernel, [parts][n_z][128][128])
-__global__ void reduce_w0_block_kernel(const float* __restrict__ partial, int parts, int n_z, int z, float* __restrict__ gW0, int ld, int col0) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kD * kD) return;
-  gW0[int64_t(i / kD) * ld + col0 + (i % kD)] = ordered_sum(partial + int64_t(z) * kD * kD + i, parts, int64_t(n_z) * kD * kD);
+__global__ void __launch_bounds__(256)
+reduce_w0_block_kernel(const float* __restrict__ partial, int parts, int n_z, int z, float* __restrict__ gW0, int ld, int col0) {
+  __shared__ float sm[256];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = ordered_sum_block8(i < kD * kD ? partial + int64_t(z) * kD * kD + i : nullptr, parts, int64_t(n_z) * kD * kD, sm);
+  if (threadIdx.x < 32 && i < kD * kD) gW0[int64_t(i / kD) * ld + col0 + (i % kD)] = s;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
 void launch_edge_bwd_reduce(const float* w_partial, const float* epi_colpart, const float* prod_colpart, int parts, int w0_chunks, int w0_chunk0,
                             float* gW0, float* gW1, float* gW2, float* gb0, float* gb1, float* gb2, float* ggamma, float* gbeta, cudaStream_t st) {
-  edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(w_partial, epi_colpart, prod_colpart, parts, w0_chunks, w0_chunk0, 0,
+  edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 31) / 32, 256, 0, st>>>(w_partial, epi_colpart, prod_colpart, parts, w0_chunks, w0_chunk0, 0,
                                                                             gW0, gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
 }
 
@@ -825,8 +835,8 @@ int edge_project_backward_tc(int64_t num_nodes, const void* v, const void* packe
   if (int rc = tc_pair_wgrad(num_nodes, grad_s, v, grad_r, v, partial, parts, st)) return rc;
   {
     HGN_TIMED("reduce_weight_partials", st);
-    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, parts, 2, 1, grad_W0, 3 * kD, 0);        // Gs^T v -> columns 0:128
-    reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, parts, 2, 0, grad_W0, 3 * kD, kD);       // Gr^T v -> columns 128:256
+    reduce_w0_block_kernel<<<kD * kD / 32, 256, 0, st>>>(partial, parts, 2, 1, grad_W0, 3 * kD, 0);        // Gs^T v -> columns 0:128
+    reduce_w0_block_kernel<<<kD * kD / 32, 256, 0, st>>>(partial, parts, 2, 0, grad_W0, 3 * kD, kD);       // Gr^T v -> columns 128:256
   }
   HGN_LAUNCH_OK("edge_project_backward reductions");
   return HGN_OK;
@@ -921,7 +931,7 @@ static int projected_backward_launch(int64_t rows, const void* dense, const void
   }
   {
     HGN_TIMED("reduce_weight_partials", st);
-    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 255) / 256, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, a.w0_chunks, a.w0_chunk0, 0,
+    edge_bwd_reduce_kernel<<<(3 * kD * kD + 5 * kD + 31) / 32, 256, 0, st>>>(a.w_partial, a.epi_colpart, a.prod_colpart, L.grid, a.w0_chunks, a.w0_chunk0, 0,
                                                                               gW0, gW1, gW2, gb0, gb1, gb2, ggamma, gbeta);
   }
   HGN_LAUNCH_OK("edge_bwd_reduce");
@@ -996,8 +1006,8 @@ int node_update_backward_tc(int64_t num_nodes, const void* v, int n_agg, const v
     if (int rc = tc_pair_wgrad(num_nodes, g0, aggs[2 * t], n == 2 ? g0 : nullptr, n == 2 ? aggs[2 * t + 1] : nullptr, partial, L.parts, st)) return rc;
     {
       HGN_TIMED("reduce_weight_partials", st);
-      reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 1, gW0, w0_chunks * kD, (1 + 2 * t) * kD);
-      if (n == 2) reduce_w0_block_kernel<<<kD * kD / 256, 256, 0, st>>>(partial, L.parts, 2, 0, gW0, w0_chunks * kD, (2 + 2 * t) * kD);
+      reduce_w0_block_kernel<<<kD * kD / 32, 256, 0, st>>>(partial, L.parts, 2, 1, gW0, w0_chunks * kD, (1 + 2 * t) * kD);
+      if (n == 2) reduce_w0_block_kernel<<<kD * kD / 32, 256, 0, st>>>(partial, L.parts, 2, 0, gW0, w0_chunks * kD, (2 + 2 * t) * kD);
     }
     HGN_LAUNCH_OK("node_update_backward reductions");
   }

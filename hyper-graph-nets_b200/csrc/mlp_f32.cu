@@ -469,20 +469,25 @@ mlp_wgrad_f32_kernel(int64_t rows, int64_t slab0, int64_t slab_rows, int rows_pe
   }
 }
 
-// out[i] = sum_p in[p*stride + i]  (fixed order)
-__global__ void reduce_parts_kernel(const float* __restrict__ in, int parts, int64_t stride, int64_t n, float* __restrict__ out) {
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= n) return;
-  out[i] = ordered_sum(in + i, parts, stride);
+// out[i] = sum_p in[p*stride + i]  (fixed order; 32 outputs per 256-thread block, common.cuh ordered_sum_block8)
+__global__ void __launch_bounds__(256)
+reduce_parts_kernel(const float* __restrict__ in, int parts, int64_t stride, int64_t n, float* __restrict__ out) {
+  __shared__ float sm[256];
+  const int64_t i = blockIdx.x * int64_t(32) + (threadIdx.x & 31);
+  const float s = ordered_sum_block8(i < n ? in + i : nullptr, parts, stride, sm);
+  if (threadIdx.x < 32 && i < n) out[i] = s;
 }
 // dW0[o][c*128 + i] = sum_p partial[p][z=c][o][i]
-__global__ void reduce_w0_kernel(const float* __restrict__ partial, int parts, int n_z, int n_chunks, float* __restrict__ dW0) {
+__global__ void __launch_bounds__(256)
+reduce_w0_kernel(const float* __restrict__ partial, int parts, int n_z, int n_chunks, float* __restrict__ dW0) {
+  __shared__ float sm[256];
   const int64_t k0 = int64_t(n_chunks) * kD;
-  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= kD * k0) return;
-  const int64_t o = i / k0, col = i - o * k0;
+  const int64_t i = blockIdx.x * int64_t(32) + (threadIdx.x & 31);
+  const bool on = i < kD * k0;
+  const int64_t o = on ? i / k0 : 0, col = on ? i - o * k0 : 0;
   const int c = int(col / kD), ii = int(col - int64_t(c) * kD);
-  dW0[i] = ordered_sum(partial + (int64_t(c) * kD + o) * kD + ii, parts, int64_t(n_z) * kD * kD);
+  const float s = ordered_sum_block8(on ? partial + (int64_t(c) * kD + o) * kD + ii : nullptr, parts, int64_t(n_z) * kD * kD, sm);
+  if (threadIdx.x < 32 && on) dW0[i] = s;
 }
 
 // partial layout [parts][n_chunks + 2][128][128]: z < n_chunks -> W0 chunk z ; n_chunks -> W1 ; n_chunks + 1 -> W2
@@ -490,9 +495,9 @@ void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks
   const int n_z = n_chunks + 2;
   const int64_t k0 = int64_t(n_chunks) * kD, blk = int64_t(kD) * kD;
   HGN_TIMED("reduce_weight_partials", st);
-  reduce_w0_kernel<<<unsigned(ceil_div(kD * k0, 256)), 256, 0, st>>>(partial, parts, n_z, n_chunks, gW0);
-  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks) * blk, parts, int64_t(n_z) * blk, blk, gW1);
-  reduce_parts_kernel<<<unsigned(ceil_div(blk, 256)), 256, 0, st>>>(partial + int64_t(n_chunks + 1) * blk, parts, int64_t(n_z) * blk, blk, gW2);
+  reduce_w0_kernel<<<unsigned(ceil_div(kD * k0, 32)), 256, 0, st>>>(partial, parts, n_z, n_chunks, gW0);
+  reduce_parts_kernel<<<unsigned(ceil_div(blk, 32)), 256, 0, st>>>(partial + int64_t(n_chunks) * blk, parts, int64_t(n_z) * blk, blk, gW1);
+  reduce_parts_kernel<<<unsigned(ceil_div(blk, 32)), 256, 0, st>>>(partial + int64_t(n_chunks + 1) * blk, parts, int64_t(n_z) * blk, blk, gW2);
 }
 
 struct BwdLayoutF32 {
@@ -591,11 +596,11 @@ int mlp_f32_backward(int64_t rows, const hgn_chunks* ch, const void* packed, con
     if (rows == 0) break;
   }
   launch_reduce_weight_partials(partial, int(L.parts), nch, gW0, gW1, gW2, st);
-  reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial, int(L.parts), 3 * kD, kD, gb0);
-  reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial + kD, int(L.parts), 3 * kD, kD, gb1);
-  reduce_parts_kernel<<<1, 128, 0, st>>>(bias_partial + 2 * kD, int(L.parts), 3 * kD, kD, gb2);
-  reduce_parts_kernel<<<1, 128, 0, st>>>(ln_partial, int(L.tiles), 256, kD, ggamma);
-  reduce_parts_kernel<<<1, 128, 0, st>>>(ln_partial + kD, int(L.tiles), 256, kD, gbeta);
+  reduce_parts_kernel<<<kD / 32, 256, 0, st>>>(bias_partial, int(L.parts), 3 * kD, kD, gb0);
+  reduce_parts_kernel<<<kD / 32, 256, 0, st>>>(bias_partial + kD, int(L.parts), 3 * kD, kD, gb1);
+  reduce_parts_kernel<<<kD / 32, 256, 0, st>>>(bias_partial + 2 * kD, int(L.parts), 3 * kD, kD, gb2);
+  reduce_parts_kernel<<<kD / 32, 256, 0, st>>>(ln_partial, int(L.tiles), 256, kD, ggamma);
+  reduce_parts_kernel<<<kD / 32, 256, 0, st>>>(ln_partial + kD, int(L.tiles), 256, kD, gbeta);
   HGN_LAUNCH_OK("mlp_bwd_f32 reductions");
   return HGN_OK;
 }

@@ -815,17 +815,12 @@ static BwdLayoutTc bwd_layout_tc(int64_t rows, int n_chunks) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   for (int i = 0; i < 6; ++i) L.act[i] = take(size_t(L.slab_rows) * kD * 2);
   L.partial = take(size_t(L.parts) * L.n_z * kD * kD * 4);
-  L.vec_partial = take(size_t(ceil_div(L.slab_rows, 2048)) * kD * 4 + 5 * kD * 4 * 2);
+  L.vec_partial = take(colsum5_workspace_bytes(L.slab_rows));
   L.total = off;
   return L;
 }
 
 size_t mlp_tc_backward_workspace_bytes(int64_t rows, int n_chunks) { return bwd_layout_tc(rows, n_chunks).total; }
-
-__global__ void axpy_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = accumulate ? dst[i] + src[i] : src[i];
-}
 
 int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* grad_out, int resid_chunk,
                     void* const* grad_chunk, float* gW0, float* gb0, float* gW1, float* gb1, float* gW2, float* gb2,
@@ -846,8 +841,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
   { const char* ab = getenv("HGN_TC_ABLATE"); bw.ablate = ab ? atoi(ab) : 0; }
   float* partial = (float*)(ws + L.partial);
   float* vec_ws = (float*)(ws + L.vec_partial);
-  float* vec_tmp = vec_ws + ceil_div(L.slab_rows, 2048) * kD;   // 5 x 128 staging for per-slab column sums
-  const size_t colsum_ws_bytes = size_t(ceil_div(L.slab_rows, 2048)) * kD * 4;
+  const size_t colsum_ws_bytes = colsum5_workspace_bytes(L.slab_rows);
   WgradArgs wa{};
   wa.G2 = bw.G2; wa.G1 = bw.G1; wa.G0 = bw.G0; wa.H1 = bw.H1; wa.H2 = bw.H2;
   wa.partial = partial; wa.n_z = L.n_z;
@@ -873,11 +867,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
     HGN_LAUNCH_OK("mlp_wgrad_tc");
     // bias / LayerNorm vector gradients: column sums of G2, G1, G0, P and grad_out over this slab
     const void* mats[5] = {bw.G2, bw.G1, bw.G0, bw.P, bw.grad_out ? (const void*)(bw.grad_out + slab0 * kD) : nullptr};
-    for (int i = 0; i < 5; ++i) {
-      float* dst = pass == 0 ? vec_out[i] : vec_tmp + i * kD;
-      if (int rc = hgn_colsum(HGN_BF16, mats[i], this_rows > 0 ? this_rows : 0, kD, dst, vec_ws, colsum_ws_bytes, st)) return rc;
-      if (pass > 0) axpy_vec_kernel<<<1, 128, 0, st>>>(vec_out[i], dst, kD, 1);
-    }
+    if (int rc = colsum5_bf16(mats, vec_out, this_rows > 0 ? this_rows : 0, pass > 0, vec_ws, colsum_ws_bytes, st)) return rc;
     if (rows == 0) break;
   }
   launch_reduce_weight_partials(partial, int(L.parts), nch, gW0, gW1, gW2, st);

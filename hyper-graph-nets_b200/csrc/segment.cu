@@ -524,6 +524,66 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t b
 }
 }  // namespace hgn
 
+// ---- the five vector gradients of one generic bf16 MLP backward (column sums of G2, G1, G0, P, grad_out: [rows,128] bf16 each) in
+// two launches instead of ten: grid (row blocks, matrix); 16 threads per row (8 columns = 16 bytes each), 16 row lanes, four row
+// loads in flight per thread; fixed-order shared-memory combine, then a fixed-order sum over the row blocks (ordered_sum_block8).
+namespace hgn {
+constexpr int kColsum5Rows = 512;
+struct Colsum5Args { const __nv_bfloat16* x[5]; float* out[5]; };
+
+__global__ void __launch_bounds__(256)
+colsum5_partial_kernel(Colsum5Args a, int64_t rows, float* __restrict__ partial) {
+  __shared__ float red[16][128];
+  const __nv_bfloat16* x = a.x[blockIdx.y];
+  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int64_t r0 = int64_t(blockIdx.x) * kColsum5Rows, r1 = min(rows, r0 + kColsum5Rows);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (x != nullptr) {
+    for (int64_t r = r0 + ry; r < r1; r += 64) {
+      uint4 w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = r + 16 * k < r1 ? __ldg(reinterpret_cast<const uint4*>(x + (r + 16 * k) * 128 + cx * 8)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t u[4] = {w[k].x, w[k].y, w[k].z, w[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[2 * j] += __uint_as_float(u[j] << 16); s[2 * j + 1] += __uint_as_float(u[j] & 0xFFFF0000u); }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cx * 8 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) t += red[l][threadIdx.x];
+    partial[(int64_t(blockIdx.y) * gridDim.x + blockIdx.x) * 128 + threadIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum5_final_kernel(Colsum5Args a, const float* __restrict__ partial, int blocks, int accumulate) {
+  __shared__ float sm[256];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float t = ordered_sum_block8(partial + int64_t(blockIdx.y) * blocks * 128 + c, blocks, 128, sm);
+  if (threadIdx.x < 32) { float* o = a.out[blockIdx.y]; o[c] = accumulate ? o[c] + t : t; }
+}
+
+size_t colsum5_workspace_bytes(int64_t rows) { return size_t(ceil_div(rows > 0 ? rows : 1, kColsum5Rows)) * 5 * 128 * 4; }
+
+int colsum5_bf16(const void* const* mats, float* const* outs, int64_t rows, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int64_t blocks = ceil_div(rows > 0 ? rows : 1, kColsum5Rows);
+  if (workspace_bytes < size_t(blocks) * 5 * 128 * 4 || !workspace) { set_error("colsum5: workspace too small"); return HGN_ERR_WORKSPACE; }
+  Colsum5Args a{};
+  for (int i = 0; i < 5; ++i) { a.x[i] = rows > 0 ? static_cast<const __nv_bfloat16*>(mats[i]) : nullptr; a.out[i] = outs[i]; }
+  HGN_TIMED("colsum", st);
+  colsum5_partial_kernel<<<dim3(unsigned(blocks), 5), 256, 0, st>>>(a, rows, static_cast<float*>(workspace));
+  colsum5_final_kernel<<<dim3(4, 5), 256, 0, st>>>(a, static_cast<const float*>(workspace), int(blocks), accumulate);
+  HGN_LAUNCH_OK("colsum5");
+  return HGN_OK;
+}
+}  // namespace hgn
+
 extern "C" size_t hgn_colsum_workspace_bytes(int64_t rows, int32_t D) {
   return size_t(hgn::ceil_div(rows > 0 ? rows : 1, hgn::kColsumRowsPerBlock)) * size_t(D) * 4;
 }

@@ -107,6 +107,8 @@ int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, c
 int tc_sm_count();                 // SMs of the current device (mlp_tc.cu)
 uint32_t* debug_buffer_device();   // cabi.cu: host-mapped words, readable after a device trap
 // fixed-order reductions of the per-CTA weight-gradient partials (mlp_f32.cu)
+size_t colsum5_workspace_bytes(int64_t rows);                                  // segment.cu
+int colsum5_bf16(const void* const* mats, float* const* outs, int64_t rows, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void launch_reduce_weight_partials(const float* partial, int parts, int n_chunks, float* gW0, float* gW1, float* gW2, cudaStream_t st);
 
 }  // namespace hgn

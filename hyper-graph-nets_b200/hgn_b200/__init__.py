@@ -8,6 +8,12 @@ symbols so the reference's own system models (``FlagModel`` ...) run on it uncha
 """
 from .config import precision, set_precision  # noqa: F401
 
+
+def invalidate_packed_weights() -> None:
+    """See ``hgn_b200.ops.invalidate_packed_weights`` (needed only after writes through ``Parameter.data``)."""
+    from . import ops
+    ops.invalidate_packed_weights()
+
 __version__ = '0.1.0'
 
 

@@ -126,11 +126,21 @@ class MLPCall:
         self.rows, self.chunks, self.resid_source, self.resid_offset, self.packed_cache = rows, chunks, resid_source, resid_offset, packed_cache
 
 
+_PACK_EPOCH = [0]
+
+
+def invalidate_packed_weights() -> None:
+    """Drop every staged (packed bf16 / fp32) weight copy.  The staged copies follow ``Parameter._version`` (optimizer steps,
+    ``load_state_dict``, in-place ops); writes through ``p.data`` (``p.data.copy_()``, EMA swaps, manual loading) do not bump it --
+    call this after such a write."""
+    _PACK_EPOCH[0] += 1
+
+
 def _pack_weights(cache: dict, dtype: torch.dtype, n_chunks: int, params: Sequence[torch.Tensor]) -> torch.Tensor:
     """Layout/precision conversion of the eight parameter tensors, redone only when a parameter changed
     (optimizer steps bump ``_version``)."""
     key = (dtype, n_chunks)
-    versions = tuple((p.data_ptr(), p._version) for p in params)
+    versions = (_PACK_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
     hit = cache.get(key)
     # While a CUDA graph is being captured the pack kernel always becomes part of the graph: a replay must re-read the master
     # weights the (captured) optimizer step has changed, and the host-side version check does not run at replay time.
