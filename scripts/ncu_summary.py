@@ -45,7 +45,10 @@ if "--json" in sys.argv:
         entry = kernels.setdefault(short, {"launches": 0, "dram_bytes_per_launch": 0.0})
         entry["launches"] += 1
         entry["dram_bytes_per_launch"] += rd + wr
-        entry["duration_us_profiled"] = num(r, "gpu__time_duration.sum")
+        dur = num(r, "gpu__time_duration.sum")
+        dunit = units[ix["gpu__time_duration.sum"]].lower()
+        entry["duration_us_profiled"] = None if dur is None else dur * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(dunit, 1.0)
+        entry["l1_lsu_data_pipe_pct"] = num(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed")
         entry["tensor_pipe_active_pct"] = num(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
         entry["dram_throughput_pct"] = num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
         entry["issue_active_pct"] = num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")
