@@ -234,12 +234,11 @@ __global__ void rows_scatter_kernel(const T* __restrict__ src, const int32_t* __
 // projected edge backward): half a warp per segment, 16 bytes per lane and row, the segment's element ids fetched with one
 // coalesced load and up to eight row loads in flight per lane (mean in-degree ~6 on triangle meshes, so most segments are a
 // single round).  Summation order = ascending position in `perm` (= ascending element id), like the generic kernel.
-__global__ void __launch_bounds__(256)
-segment_sum_bf16_128_kernel(const __nv_bfloat16* __restrict__ data, const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
-                            int64_t S, __nv_bfloat16* __restrict__ out_sum, int accumulate_sum) {
+__device__ __forceinline__ void
+segment_sum_bf16_128_body(const __nv_bfloat16* __restrict__ data, const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
+                          int64_t S, __nv_bfloat16* __restrict__ out_sum, int accumulate_sum, int64_t seg) {
   const int l16 = threadIdx.x & 15;
   const uint32_t hmask = 0xFFFFu << (threadIdx.x & 16);     // the two halves of a warp run different trip counts
-  const int64_t seg = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 4;
   const bool live = seg < S;
   const int beg = live ? rowptr[seg] : 0, end = live ? rowptr[seg + 1] : 0;
   float acc[8];
@@ -279,6 +278,25 @@ segment_sum_bf16_128_kernel(const __nv_bfloat16* __restrict__ data, const int32_
     o[i] = *reinterpret_cast<uint32_t*>(&t);
   }
   *op = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256)
+segment_sum_bf16_128_kernel(const __nv_bfloat16* __restrict__ data, const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
+                            int64_t S, __nv_bfloat16* __restrict__ out_sum, int accumulate_sum) {
+  segment_sum_bf16_128_body(data, perm, rowptr, S, out_sum, accumulate_sum, (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 4);
+}
+
+// Two sums of the SAME rows under two groupings (the sender-keyed and the receiver-keyed sum of G0 in the projected edge backward):
+// even blocks take grouping A, odd blocks grouping B, over the same range of segments, so the two reads of a row fall close together in
+// time.  On a mesh whose node numbering is local (an edge's endpoints are near each other in the numbering) the second read of each row
+// is an L2 hit: the pair moves E*256 B from HBM once instead of twice.  Arithmetic and order per segment are those of the single kernel.
+__global__ void __launch_bounds__(256)
+segment_sum_pair_bf16_128_kernel(const __nv_bfloat16* __restrict__ data, const int32_t* __restrict__ perm_a, const int32_t* __restrict__ rowptr_a,
+                                 int64_t S_a, __nv_bfloat16* __restrict__ out_a, const int32_t* __restrict__ perm_b,
+                                 const int32_t* __restrict__ rowptr_b, int64_t S_b, __nv_bfloat16* __restrict__ out_b) {
+  const int64_t seg = ((blockIdx.x >> 1) * int64_t(blockDim.x) + threadIdx.x) >> 4;
+  if (blockIdx.x & 1) segment_sum_bf16_128_body(data, perm_b, rowptr_b, S_b, out_b, 0, seg);
+  else segment_sum_bf16_128_body(data, perm_a, rowptr_a, S_a, out_a, 0, seg);
 }
 
 template <typename T>
@@ -444,6 +462,23 @@ extern "C" int hgn_segment_reduce(int dtype, const void* data, int64_t E, int32_
                                               argmin, accumulate_sum, st);
   set_error("segment_reduce: unknown dtype %d", dtype);
   return HGN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hgn_segment_sum_pair(int dtype, const void* data, int64_t E, int32_t D, const int32_t* perm_a, const int32_t* rowptr_a, int64_t S_a,
+                                    void* out_a, const int32_t* perm_b, const int32_t* rowptr_b, int64_t S_b, void* out_b, void* stream) {
+  HGN_CHECK_ARG(D >= 1 && E >= 0 && S_a >= 0 && S_b >= 0, "segment_sum_pair: bad sizes");
+  HGN_CHECK_ARG(rowptr_a && rowptr_b && out_a && out_b && (E == 0 || (data && perm_a && perm_b)), "segment_sum_pair: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == HGN_BF16 && D == 128 && S_a > 0 && S_b > 0) {
+    const int64_t blocks = ceil_div((S_a > S_b ? S_a : S_b) * 16, 256);
+    HGN_TIMED("segment_reduce", st);
+    segment_sum_pair_bf16_128_kernel<<<unsigned(2 * blocks), 256, 0, st>>>((const __nv_bfloat16*)data, perm_a, rowptr_a, S_a, (__nv_bfloat16*)out_a,
+                                                                        perm_b, rowptr_b, S_b, (__nv_bfloat16*)out_b);
+    HGN_LAUNCH_OK("segment_sum_pair");
+    return HGN_OK;
+  }
+  if (int rc = hgn_segment_reduce(dtype, data, E, D, perm_a, rowptr_a, S_a, out_a, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream)) return rc;
+  return hgn_segment_reduce(dtype, data, E, D, perm_b, rowptr_b, S_b, out_b, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int hgn_segment_reduce_bwd(int dtype, int64_t E, int32_t D, const int32_t* ids32, const int32_t* perm, const int32_t* rowptr, int64_t S,

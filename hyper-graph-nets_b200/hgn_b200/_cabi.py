@@ -14,7 +14,7 @@ HGN_F32 = 0
 HGN_BF16 = 1
 AGG_SUM, AGG_MEAN, AGG_MAX, AGG_MIN = 1, 2, 4, 8
 HGN_MAX_CHUNKS = 24
-ABI_VERSION = 5            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
+ABI_VERSION = 6            # HGN_B200_ABI_VERSION of include/hgn_b200.h these signatures were written against
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhgn_b200.so")
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     "hgn_csr_build": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hgn_segment_reduce": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "hgn_segment_sum_pair": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "hgn_segment_reduce_bwd": (c_int, [c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hgn_multi_segment_sum": (c_int, [c_int, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -393,11 +393,10 @@ class _EdgeUpdate(torch.autograd.Function):
                 *[g.data_ptr() for g in gparams], ws.data_ptr(), ws_bytes, _cabi.stream_ptr()), "hgn_edge_update_backward")
             _count(2)
             # d loss / d Ps, d Pr: sender- and receiver-keyed segment sums of G0 (deterministic CSR passes)
-            for plan, dst in ((s_plan, gs), (r_plan, gr)):
-                _cabi.check(lib.hgn_segment_reduce(_cabi.HGN_BF16, g0.data_ptr(), E, D_LATENT, plan.perm.data_ptr(), plan.rowptr.data_ptr(),
-                                                   n, dst.data_ptr(), None, None, None, None, None, 0, _cabi.stream_ptr()),
-                            "hgn_segment_reduce")
-                _count()
+            _cabi.check(lib.hgn_segment_sum_pair(_cabi.HGN_BF16, g0.data_ptr(), E, D_LATENT, s_plan.perm.data_ptr(), s_plan.rowptr.data_ptr(), n,
+                                                 gs.data_ptr(), r_plan.perm.data_ptr(), r_plan.rowptr.data_ptr(), n, gr.data_ptr(),
+                                                 _cabi.stream_ptr()), "hgn_segment_sum_pair")
+            _count()
         return (gs, gr, grad_e, *gparams, None, None, None, None)
 
 
@@ -548,13 +547,12 @@ class _GraphNetSumLayer(torch.autograd.Function):
             _cabi.check(lib.hgn_edge_update_backward(BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(),
                                                      packed_e.data_ptr(), _cabi.ptr(grad_e_new), grad_agg.data_ptr(), grad_e.data_ptr(), g0.data_ptr(),
                                                      *[g.data_ptr() for g in ge], ws.data_ptr(), ws_bytes, st), "hgn_edge_update_backward")
-            for plan, dst in ((s_plan, gs), (r_plan, gr)):
-                _cabi.check(lib.hgn_segment_reduce(BF, g0.data_ptr(), E, D_LATENT, plan.perm.data_ptr(), plan.rowptr.data_ptr(), n, dst.data_ptr(),
-                                                   None, None, None, None, None, 0, st), "hgn_segment_reduce")
+            _cabi.check(lib.hgn_segment_sum_pair(BF, g0.data_ptr(), E, D_LATENT, s_plan.perm.data_ptr(), s_plan.rowptr.data_ptr(), n, gs.data_ptr(),
+                                                 r_plan.perm.data_ptr(), r_plan.rowptr.data_ptr(), n, gr.data_ptr(), st), "hgn_segment_sum_pair")
             # the edge backward wrote only the We block of d W0 (columns 256:384); the node-level kernel fills columns 0:256
             _cabi.check(lib.hgn_edge_project_backward(BF, n, v.data_ptr(), packed_e.data_ptr(), gs.data_ptr(), gr.data_ptr(), grad_v_node.data_ptr(),
                                                       grad_v.data_ptr(), ge[0].data_ptr(), ws.data_ptr(), ws_bytes, st), "hgn_edge_project_backward")
-        _count(5 + 2 + 2 + 4)
+        _count(5 + 2 + 1 + 4)
         return (grad_v, grad_e, None, None, None, None, *ge, *gn)
 
 

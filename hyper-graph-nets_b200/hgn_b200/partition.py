@@ -410,9 +410,8 @@ class _PeerEdgeUpdate(torch.autograd.Function):
                 BF, E, e.data_ptr(), ps.data_ptr(), pr.data_ptr(), s_plan.ids32.data_ptr(), r_plan.ids32.data_ptr(), ctx.packed.data_ptr(),
                 _cabi.ptr(grad_out), _cabi.ptr(grad_agg), grad_e.data_ptr(), g0.data_ptr(), *[g.data_ptr() for g in gp], ws.data_ptr(),
                 ws_bytes, st), "hgn_edge_update_backward")
-            for plan, n_seg, dst in ((s_plan, No + G, gs), (r_plan, No, gr)):
-                _cabi.check(lib.hgn_segment_reduce(BF, g0.data_ptr(), E, D, plan.perm.data_ptr(), plan.rowptr.data_ptr(), n_seg, dst.data_ptr(),
-                                                   None, None, None, None, None, 0, st), "hgn_segment_reduce")
+            _cabi.check(lib.hgn_segment_sum_pair(BF, g0.data_ptr(), E, D, s_plan.perm.data_ptr(), s_plan.rowptr.data_ptr(), No + G, gs.data_ptr(),
+                                                 r_plan.perm.data_ptr(), r_plan.rowptr.data_ptr(), No, gr.data_ptr(), st), "hgn_segment_sum_pair")
             halo.push_backward(step, layer, gs)              # ghost rows of gs go home; the rows of this rank's boundary nodes arrive
             inbox = halo.inbox(layer)
             lo = 0
@@ -428,7 +427,7 @@ class _PeerEdgeUpdate(torch.autograd.Function):
                                                       grad_owned.data_ptr(), gp[0].data_ptr(), pws.data_ptr(), pws_bytes, st),
                         "hgn_edge_project_backward")
         from . import ops as _ops
-        _ops._count(12)
+        _ops._count(11)
         return (grad_owned, grad_e, *gp, None, None, None, None)
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HGN_B200_ABI_VERSION 5
+#define HGN_B200_ABI_VERSION 6
 
 typedef enum {
   HGN_OK = 0,
@@ -74,6 +74,15 @@ int hgn_segment_reduce(int dtype, const void* data, int64_t num_edges, int32_t D
                        const int32_t* perm, const int32_t* rowptr, int64_t num_segments,
                        void* out_sum, void* out_mean, void* out_max, void* out_min,
                        int32_t* argmax, int32_t* argmin, int accumulate_sum, void* stream);
+
+/* 'sum' of the same rows under two groupings in one pass (out_a[S_a,D] by (perm_a,rowptr_a), out_b[S_b,D] by (perm_b,rowptr_b)):
+ * the autograd of the two row gathers v[senders], v[receivers] of one edge set (src/migration/graphnet.py:24-25: index_select ->
+ * two index_add_) applied to the same per-edge gradient.  Same arithmetic and summation order as two hgn_segment_reduce calls; for
+ * bf16 / D = 128 the two groupings are interleaved block by block so that, on a mesh with local node numbering, each row is read
+ * from HBM once. */
+int hgn_segment_sum_pair(int dtype, const void* data, int64_t num_edges, int32_t D,
+                         const int32_t* perm_a, const int32_t* rowptr_a, int64_t num_segments_a, void* out_a,
+                         const int32_t* perm_b, const int32_t* rowptr_b, int64_t num_segments_b, void* out_b, void* stream);
 
 /* Backward of the above (autograd of scatter_add / scatter_mean / scatter_max / scatter_min):
  * grad_data[e,:] (+)= g_sum[r_e,:] + g_mean[r_e,:]/max(cnt_r,1) + [argmax[r_e,:]==e] g_max[r_e,:]

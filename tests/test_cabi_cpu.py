@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/hgn_b200.h but not exported"
     assert sorted(_cabi.SIGNATURES) == declared, "ctypes signatures out of sync with the header"
-    assert lib.hgn_abi_version() == _cabi.ABI_VERSION == 5
+    assert lib.hgn_abi_version() == _cabi.ABI_VERSION == 6
 
 
 def test_size_queries_need_no_gpu():

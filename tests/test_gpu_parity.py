@@ -477,3 +477,26 @@ def test_invalidate_packed_weights_after_a_write_through_data():
     with torch.no_grad():
         fresh = ops.fused_mlp(params, {}, [x], [ops.ChunkSpec(0)], 300, resid_source=0)
     assert torch.equal(second, fresh)
+
+
+@pytest.mark.parametrize("E,Sa,Sb", [(1, 1, 1), (1000, 300, 37), (9282, 1600, 1601), (200_000, 40_000, 33_333)])
+def test_segment_sum_pair_equals_two_segment_sums_bitwise(E, Sa, Sb):
+    """hgn_segment_sum_pair (one interleaved pass, sender- and receiver-keyed sums of the same rows) == two hgn_segment_reduce calls,
+    bit for bit, for different segment counts, empty segments and ragged block counts."""
+    lib = _cabi.load()
+    rng = np.random.default_rng(E)
+    x = torch.from_numpy(rng.standard_normal((E, 128)).astype(np.float32)).cuda().to(torch.bfloat16)
+    ia = torch.from_numpy(rng.integers(0, max(Sa - 1, 1), size=E).astype(np.int64)).cuda()     # the last segment of A stays empty
+    ib = torch.from_numpy(rng.integers(0, Sb, size=E).astype(np.int64)).cuda()
+    pa, pb = segment_plan(ia, Sa), segment_plan(ib, Sb)
+    st = _cabi.stream_ptr()
+    ref_a, ref_b = torch.empty(Sa, 128, dtype=torch.bfloat16, device="cuda"), torch.empty(Sb, 128, dtype=torch.bfloat16, device="cuda")
+    for plan, S, out in ((pa, Sa, ref_a), (pb, Sb, ref_b)):
+        _cabi.check(lib.hgn_segment_reduce(_cabi.HGN_BF16, x.data_ptr(), E, 128, plan.perm.data_ptr(), plan.rowptr.data_ptr(), S, out.data_ptr(),
+                                           None, None, None, None, None, 0, st), "hgn_segment_reduce")
+    out_a, out_b = torch.full_like(ref_a, float("nan")), torch.full_like(ref_b, float("nan"))
+    _cabi.check(lib.hgn_segment_sum_pair(_cabi.HGN_BF16, x.data_ptr(), E, 128, pa.perm.data_ptr(), pa.rowptr.data_ptr(), Sa, out_a.data_ptr(),
+                                         pb.perm.data_ptr(), pb.rowptr.data_ptr(), Sb, out_b.data_ptr(), st), "hgn_segment_sum_pair")
+    assert torch.equal(out_a.view(torch.int16), ref_a.view(torch.int16)) and torch.equal(out_b.view(torch.int16), ref_b.view(torch.int16))
+    want = torch.zeros(Sa, 128, device="cuda").index_add_(0, ia, x.float())
+    assert rel_err(out_a.float(), want) < 2e-2
