@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi topo -m 2>/dev/null | head -12
 timeout 600 python -m pytest tests/test_partition_gpu.py -m gpu -q -s -x > gpurun_out/r2_partition_pytest_n$N.log 2>&1; echo "partition pytest rc=$?"; grep "PARTITION-GPU-OK\|passed\|failed\|skipped" gpurun_out/r2_partition_pytest_n$N.log | cut -c1-300; grep -B2 -A12 "Error\|error" gpurun_out/r2_partition_pytest_n$N.log | tail -30 | cut -c1-300
-for mode in peer nccl; do
+for mode in ${2:-peer nccl}; do
   HGN_HALO=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n${N}_$mode.json 2> gpurun_out/r2_bench_n${N}_$mode.err; echo "bench $mode rc=$?"
   python - <<PY
 import json

@@ -65,7 +65,10 @@ for step in range(3):
     a, b = run(fast, shift), run(generic, shift)
     errs = [rel(x, y) for x, y in zip(a, b)]
     worst_paths = max(worst_paths, max(errs))
-    assert max(errs) < 5e-3, (step, errs)          # same arithmetic; the ghost contributions are summed in another order
+    # the peer path is the fused layer (the node update's share of d loss / d v is added in fp32 inside the dgrad kernel), the NCCL path the
+    # generic block on [owned | ghost] rows (two bf16 partial gradients added by autograd): one rounding point differs per layer
+    # (measured 6.4e-3 worst over 5 layers)
+    assert max(errs) < 2e-2, (step, errs)
     if rank == 0:                                   # the whole mesh on this one GPU
         for p in params:
             p.grad = None
@@ -77,7 +80,7 @@ for step in range(3):
         single = [out.node_features[0].detach()[own], out.edge_sets[0].features.detach().float()[eid], vf.grad[own], ef.grad[eid]] + [p.grad.clone() for p in params]
         errs1 = [rel(x, y) for x, y in zip(a, single)]
         worst_single = max(worst_single, max(errs1))
-        assert max(errs1) < 1e-2, (step, errs1)
+        assert max(errs1) < 5e-3, (step, errs1)     # same kernels, same rounding points; the ghost contributions are summed in another order
     dist.barrier()
 print(f"PARTITION-GPU-OK rank {rank}/{world}: {lg.n_own} owned, {lg.n_ghost} ghosts, {lg.senders.numel()} edges; peer vs nccl path {worst_paths:.2e}"
       + (f"; vs the whole mesh on one GPU {worst_single:.2e}" if rank == 0 else ""), flush=True)
