@@ -847,19 +847,7 @@ int edge_fwd_tc_launch(int64_t rows, const void* dense, const void* proj_s, cons
                        const void* packed, int w0_chunks, int w0_chunk0, void* out, const char* name, cudaStream_t st);                                                                                  // edge_fwd_tc.cu
 int edge_update_forward_tc(int64_t num_edges, const void* edge, const void* proj_s, const void* proj_r, const int32_t* senders,
                            const int32_t* receivers, const void* packed, void* out, cudaStream_t st) {
-  static const bool legacy = getenv("HGN_EDGE_FWD_LEGACY") != nullptr;     // development: the generic tile kernel with a pre-add
-  if (!legacy) return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, "edge_fwd_tc", st);
-  hgn_chunks ch{};
-  ch.n_chunks = 1;
-  ch.src[0] = edge;
-  PreAdd pre{};
-  pre.proj_s = static_cast<const __nv_bfloat16*>(proj_s);
-  pre.proj_r = static_cast<const __nv_bfloat16*>(proj_r);
-  pre.senders = senders;
-  pre.receivers = receivers;
-  pre.w0_chunks = 3;
-  pre.w0_chunk0 = 2;
-  return mlp_tc_forward_pre(num_edges, &ch, packed, edge, 0, out, pre, "edge_fwd_tc_legacy", st);
+  return edge_fwd_tc_launch(num_edges, edge, proj_s, proj_r, senders, receivers, packed, 3, 2, out, "edge_fwd_tc", st);
 }
 
 struct EdgeBwdLayout { size_t w_partial, epi, prod, total; int grid; };

@@ -100,11 +100,11 @@ template <bool kBwd>
 __global__ void __launch_bounds__(kTileThreads, 1)
 mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch, const uint8_t* __restrict__ packed,
                    int w0_resident, const __nv_bfloat16* __restrict__ resid, int64_t resid_off, __nv_bfloat16* __restrict__ out,
-                   BwdArgs bw, PreAdd pre) {
+                   BwdArgs bw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nch = ch.n_chunks;
   const TileSmem S(nch, w0_resident != 0, kBwd);
-  const int w0_chunks = pre.w0_chunks > 0 ? pre.w0_chunks : nch;
+  const int w0_chunks = nch;
   const PackedTc P(w0_chunks);
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();   // SW128 atoms need 1024-byte alignment
@@ -116,7 +116,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
 
   // ---- prologue: resident weights, parameters, barriers, TMEM ------------------------------------
   {
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
     if (w0_resident)
       for (int c = 0; c < nch; ++c) load_weight_block(sbase + S.w0 + c * kChunkBytes, w0g + c * kD, k0, tid, kTileThreads);
     load_weight_block(sbase + S.w1, reinterpret_cast<const __nv_bfloat16*>(packed + P.w1), kD, tid, kTileThreads);
@@ -149,7 +149,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
     const int gt = ptid & 63;
     if (gt == 0) mbar_arrive(&bars[kBarEmpty + group]);   // the ring starts empty
     const uint32_t stage_addr = sbase + S.stages + group * S.stage_bytes;
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
     const int64_t n_slots = my_tiles * nch;
     const int c16 = gt & 15, rbase = gt >> 4;    // this thread copies 16-byte piece c16 of rows rbase + 4 j
     // all 32 source-row indices of a slot are fetched in one batch, one slot ahead of the copies
@@ -196,7 +196,7 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
     int wg_step[2] = {0, 0};
     uint32_t wg_sig[2] = {0, 0}, wg_fin[2] = {0, 0};
     uint32_t acc_busy = 0, w0b_uses = 0, idle = 0;
-    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0) + pre.w0_chunk0 * kD;
+    const __nv_bfloat16* w0g = reinterpret_cast<const __nv_bfloat16*>(packed + P.w0);
     while (done < my_tiles) {
       bool progressed = false;
       // lane 0 polls the barriers once per round and broadcasts, so the whole warp takes the same path
@@ -325,15 +325,6 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
       // ---- hidden layers: bias + ReLU -> bf16 A operand in TMEM -------------------------------
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
-        const bool add_proj = !kBwd && layer == 0 && pre.proj_s != nullptr;
-        // projected mode: rows of the two per-node tables, fetched (L2) while the layer-0 MMAs run
-        const __nv_bfloat16 *psrow = nullptr, *prrow = nullptr;
-        uint32_t pq[32];
-        if (add_proj) {
-          psrow = pre.proj_s + int64_t(valid ? __ldg(pre.senders + grow) : 0) * kD;
-          prrow = pre.proj_r + int64_t(valid ? __ldg(pre.receivers + grow) : 0) * kD;
-          ldg256(psrow, pq); ldg256(psrow + 16, pq + 8); ldg256(prrow, pq + 16); ldg256(prrow + 16, pq + 24);
-        }
         wait_acc();
         const float* bias = sparams + layer * kD;
         __nv_bfloat16* hws = kBwd ? (layer == 0 ? bw.H1 : bw.H2) + lrow * kD : nullptr;
@@ -342,22 +333,6 @@ mlp_tile_tc_kernel(int64_t rows, int64_t num_tiles, int64_t slab0, hgn_chunks ch
           uint32_t v[32];
           tmem_ld32(acc + cg * 32, v);
           tmem_ld_wait();
-          if (add_proj) {
-            uint32_t pn[32];
-            if (cg < 3) {   // next column group's table rows in flight while this one is consumed
-              ldg256(psrow + (cg + 1) * 32, pn); ldg256(psrow + (cg + 1) * 32 + 16, pn + 8);
-              ldg256(prrow + (cg + 1) * 32, pn + 16); ldg256(prrow + (cg + 1) * 32 + 16, pn + 24);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) + bf16_lo(pq[j]) + bf16_lo(pq[16 + j]));
-              v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) + bf16_hi(pq[j]) + bf16_hi(pq[16 + j]));
-            }
-            if (cg < 3) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) pq[j] = pn[j];
-            }
-          }
           uint32_t h[16];
           uint32_t m = 0;
 #pragma unroll
@@ -748,16 +723,9 @@ static int configure_kernels() {
   return HGN_OK;
 }
 
-int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
-                       const PreAdd& pre, const char* name, cudaStream_t st);
-
 int mlp_tc_forward(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
                    cudaStream_t st) {
-  return mlp_tc_forward_pre(rows, ch, packed, resid, resid_off, out, PreAdd{}, "mlp_tile_tc_fwd", st);
-}
-
-int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
-                       const PreAdd& pre, const char* name, cudaStream_t st) {
+  const char* name = "mlp_tile_tc_fwd";
   const int nch = ch->n_chunks;
   const bool resident = nch <= kMaxResidentChunks;
   const TileSmem S(nch, resident, false);
@@ -769,7 +737,7 @@ int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, c
   HGN_TIMED(name, st);
   mlp_tile_tc_kernel<false><<<grid, kTileThreads, S.total, st>>>(rows, tiles, 0, *ch, static_cast<const uint8_t*>(packed), resident ? 1 : 0,
                                                                  static_cast<const __nv_bfloat16*>(resid), resid_off,
-                                                                 static_cast<__nv_bfloat16*>(out), none, pre);
+                                                                 static_cast<__nv_bfloat16*>(out), none);
   HGN_LAUNCH_OK("mlp_fwd_tc");
   return HGN_OK;
 }
@@ -855,7 +823,7 @@ int mlp_tc_backward(int64_t rows, const hgn_chunks* ch, const void* packed, cons
       const unsigned grid = unsigned(tiles < tc_sm_count() ? tiles : tc_sm_count());
       HGN_TIMED("mlp_tile_tc_bwd", st);
       mlp_tile_tc_kernel<true><<<grid, kTileThreads, S.total, st>>>(rows, tiles, slab0, *ch, static_cast<const uint8_t*>(packed),
-                                                                    resident ? 1 : 0, nullptr, 0, nullptr, bw, PreAdd{});
+                                                                    resident ? 1 : 0, nullptr, 0, nullptr, bw);
       HGN_LAUNCH_OK("mlp_bwd_tc");
     }
     wa.accumulate = pass > 0;

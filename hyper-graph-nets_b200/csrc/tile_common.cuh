@@ -92,18 +92,6 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
 }
 
 
-// Optional "projected" first layer (edge update): layer 0 consumes only the chunks listed in `ch` (the edge rows) with the
-// W0 column block starting at chunk `w0_chunk0` of a `w0_chunks`-wide packed W0, and the epilogue adds the per-node
-// pre-projections  proj_s[senders[row]] + proj_r[receivers[row]]  (= v[s] W0[:,0:128]^T + v[r] W0[:,128:256]^T computed once
-// per NODE by proj_tc_kernel instead of once per EDGE here).  w0_chunks == 0 -> plain mode (w0_chunks = n_chunks, chunk0 = 0).
-struct PreAdd {
-  const __nv_bfloat16 *proj_s, *proj_r;
-  const int32_t *senders, *receivers;
-  int w0_chunks, w0_chunk0;
-};
-
-int mlp_tc_forward_pre(int64_t rows, const hgn_chunks* ch, const void* packed, const void* resid, int64_t resid_off, void* out,
-                       const PreAdd& pre, const char* name, cudaStream_t st);
 int tc_sm_count();                 // SMs of the current device (mlp_tc.cu)
 uint32_t* debug_buffer_device();   // cabi.cu: host-mapped words, readable after a device trap
 // fixed-order reductions of the per-CTA weight-gradient partials (mlp_f32.cu)
