@@ -377,6 +377,9 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         if (!first) wait_epi();                                  // previous tile's last epilogue has drained the accumulator
         stamp(a, t, 1);
         chain(S, sbase + kEbWe, false);  mma_commit(&bars[kEbAcc]);                                    // 0: e We^T
+        // the previous tile's dWe MMAs go behind this tile's step 0 (whose commit E0 waits for): they read C(t-1) = B(t) and S(t-1) = C(t),
+        // first overwritten by E1 / E2 of this tile, i.e. after the commits of steps 1 / 2, which cover them
+        if (!first) wgrad(dWe, buf(3, t - 1), buf(0, t - 1), t == 1);
         stamp(a, t, 2);
         wait_epi(); stamp(a, t, 3); chain(A, sbase + kEbW1, false);  mma_commit(&bars[kEbAcc]);                        // 1: H1 W1^T
         wait_epi(); stamp(a, t, 4); chain(B, sbase + kEbW2, false);  mma_commit(&bars[kEbAcc]);                        // 2: H2 W2^T
@@ -384,10 +387,13 @@ edge_bwd_tc_kernel(int64_t rows, int64_t num_tiles, const uint8_t* __restrict__ 
         // column sums anyway, and phases E3 / E4 overwrite buffers those MMAs read.  Step 5 commits right after the chain.
         wait_epi(); stamp(a, t, 5); chain(C, sbase + kEbW2, true);   wgrad(dW2, C, B, first); mma_commit(&bars[kEbAcc]);   // 3: dY W2 ; dW2
         wait_epi(); stamp(a, t, 6); chain(B, sbase + kEbW1, true);   wgrad(dW1, B, A, first); mma_commit(&bars[kEbAcc]);   // 4: dH2' W1 ; dW1
-        wait_epi(); stamp(a, t, 7); chain(C, sbase + kEbWe, true);   mma_commit(&bars[kEbAcc]); wgrad(dWe, C, S, first);   // 5: dH1' We ; dWe
+        wait_epi(); stamp(a, t, 7); chain(C, sbase + kEbWe, true);   mma_commit(&bars[kEbAcc]);                            // 5: dH1' We  (dWe: deferred)
         stamp(a, t, 8);
       }
-      if (my_tiles > 0) mma_commit(&bars[kEbFinal]);          // every MMA of this CTA, for the accumulator drain
+      if (my_tiles > 0) {
+        wgrad(dWe, buf(3, my_tiles - 1), buf(0, my_tiles - 1), my_tiles == 1);
+        mma_commit(&bars[kEbFinal]);                           // every MMA of this CTA, for the accumulator drain
+      }
     }
   } else {
     // =============================== epilogue ============================================================

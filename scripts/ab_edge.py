@@ -42,14 +42,22 @@ if "AB_CHILD" in os.environ:
            "sha": {"out": dig(out), "agg": dig(agg), "dv": dig(v.grad), "de": dig(e.grad), **{f"w{i}": dig(p.grad) for i, p in enumerate(w)}}}
     print("AB-RESULT " + json.dumps(res))
     sys.exit(0)
-old = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "hyper-graph-nets_b200", "build", "old", "libhgn_b200_old.so")
+# variants: "name=libpath" or "name=libpath,ENV=VALUE,..." (empty libpath = the in-tree library); default: build/old vs in-tree
+variants = sys.argv[1:] or ["old=" + os.path.join(ROOT, "hyper-graph-nets_b200", "build", "old", "libhgn_b200_old.so"), "new="]
 res = {}
-for tag, lib in (("old", old), ("new", "")):
-    run = subprocess.run([sys.executable, __file__], env=dict(os.environ, AB_CHILD=lib), capture_output=True, text=True, timeout=600)
+for spec in variants:
+    tag, rest = spec.split("=", 1)
+    parts = rest.split(",")
+    lib, env = parts[0], dict(kv.split("=", 1) for kv in parts[1:])
+    if lib and not os.path.isabs(lib):
+        lib = os.path.join(ROOT, lib)
+    run = subprocess.run([sys.executable, __file__], env=dict(os.environ, AB_CHILD=lib, **env), capture_output=True, text=True, timeout=600)
     line = [ln for ln in run.stdout.splitlines() if ln.startswith("AB-RESULT ")]
     if not line:
-        print(tag, "FAILED", run.stdout[-2000:], run.stderr[-3000:]); sys.exit(1)
+        print(tag, "FAILED", run.stdout[-2000:], run.stderr[-3000:]); continue
     res[tag] = json.loads(line[-1][10:])
     print(tag, res[tag]["ms"])
-same = {k: res["old"]["sha"][k] == res["new"]["sha"][k] for k in res["old"]["sha"]}
-print("bitwise identical:", all(same.values()), {k: v for k, v in same.items() if not v})
+tags = list(res)
+for t in tags[1:]:
+    same = {k: res[tags[0]]["sha"][k] == res[t]["sha"][k] for k in res[tags[0]]["sha"]}
+    print(f"{t} bitwise identical to {tags[0]}:", all(same.values()), {k: v for k, v in same.items() if not v})
