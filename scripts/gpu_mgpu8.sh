@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# usage: gpurun --gpus 8 -- bash scripts/gpu_mgpu8.sh     (N = 4 and N = 8 on one 8-GPU box)
+# usage: gpurun --gpus 8 -- bash scripts/gpu_mgpu8.sh ["4:peer 8:peer 8:nccl"]     (N = 4 and N = 8 on one 8-GPU box)
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 timeout 600 python -m pytest tests/test_partition_gpu.py -m gpu -q -s > gpurun_out/r2_partition_pytest_n8.log 2>&1; echo "partition pytest rc=$?"; grep "PARTITION-GPU-OK rank 0\|passed\|failed" gpurun_out/r2_partition_pytest_n8.log | cut -c1-300
@@ -15,6 +15,4 @@ except Exception as e:
     print('N=$1 $2: no line', e); print(open('gpurun_out/r2_bench_n$1_$2.err').read()[-1500:])
 PY
 }
-run 4 peer
-run 8 peer
-run 8 nccl
+for spec in ${1:-4:peer 8:peer 8:nccl}; do run ${spec%%:*} ${spec##*:}; done

@@ -4,6 +4,7 @@
 TAG=${1:-r2}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; grep "^smoke" gpurun_out/${TAG}_smoke.log
 timeout 900 python -m pytest tests -x -q -m gpu -s -p no:cacheprovider > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/${TAG}_pytest_gpu.log | cut -c1-250
 grep -E "^(15 layers|slab|cfg5 full|dropin\[|PARTITION|.*rerouted)" gpurun_out/${TAG}_pytest_gpu.log | cut -c1-420
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/${TAG}_bench_n1.err | cut -c1-300
