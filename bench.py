@@ -69,15 +69,55 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of one GPU sampled while the timed region runs: through NVML inside this process
+    every 20 ms (a timed region of a few hundred ms at N = 8 is over before an `nvidia-smi -lms` child has printed its first line),
+    falling back to an `nvidia-smi -lms 200` child where the NVML bindings are missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.nvml, self.handle, self.stop = None, None, threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)      # no CUDA_VISIBLE_DEVICES remapping: same numbering
+        return pynvml, handle
+
+    def _sample_nvml(self):
+        nv, h = self.nvml, self.handle
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.rows.append([sm, mx] + ["Active" if mask & bit else "Not Active" for bit, _ in self.NVML_REASONS])
+        except Exception:
+            pass
+
+    def _loop_nvml(self):
+        while not self.stop.is_set():
+            self._sample_nvml()
+            self.stop.wait(0.02)
 
     def __enter__(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -93,6 +133,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        if self.nvml is not None:
+            self._sample_nvml()                                  # one more at the end of the region (the GPU is still busy or just done)
+            self.stop.set()
+            self.thread.join(timeout=2)
+            return
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -109,12 +154,13 @@ class ClockSampler:
             except (ValueError, IndexError):
                 continue
             for name, val in zip(names, row[2:6]):
-                if val.lower().startswith("active"):
+                if str(val).lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "via": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------
