@@ -23,9 +23,11 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-2}
 # fp32: max metric.  bf16: L2 metric against the FP32 reference; the bound is loose on purpose -- with ~0.3% of
 # the ReLU pre-activations inside bf16 rounding noise of zero, about half of all rows have one of their ~64 active
-# hidden units switched relative to fp32, which moves that row's data gradient by ~1/sqrt(64) (measured 0.10-0.16
-# on the goldens).  Kernel correctness of the bf16 backward is pinned separately, at 1e-2, by
-# test_bf16_kernels_vs_bf16_emulation (same rounding points => same ReLU masks).
+# hidden units switched relative to fp32, which moves that row's data gradient by ~1/sqrt(64).  Measured on the B200
+# (printed per case with -s; profiles/r2_parity_measured.txt): 0.099 (mgn_pna_L1) .. 0.179 (hgn_hyper_sum_L2) on the one-tile
+# goldens, 0.18 .. 0.235 on the 300-node ones, 0.279 on hgn_multiscale_sum_L1 -- the bound sits 8 % above the worst case.
+# Kernel correctness of the bf16 backward is pinned separately, at 1e-2, by test_bf16_kernels_vs_bf16_emulation (same
+# rounding points => same ReLU masks; 3-4e-3 measured on the full cfg5 mesh).
 GRAD_TOL = {"fp32": 5e-5, "bf16": 3e-1}
 
 
