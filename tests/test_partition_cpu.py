@@ -86,13 +86,23 @@ def _cpu_row_kernels():
     partition._scatter_add_rows = scatter_add
 
 
-def _worker(rank, world, port, tmpdir):
+def _mesh_edges(w, h, directed):
+    """The two-way grid mesh, or only its ascending edges (sender < receiver): with a block partition the lower rank then sends boundary
+    rows but owns no ghost, and in the backward receives ghost gradients but returns none -- the asymmetric case of ADVICE r1."""
+    s, r = synthetic.grid_edges_two_way(w, h)
+    if directed:
+        keep = s < r
+        s, r = s[keep], r[keep]
+    return s, r
+
+
+def _worker(rank, world, port, tmpdir, directed=False):
     _cpu_row_kernels()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         w, h, layers = 9, 8, 2
-        s, r = synthetic.grid_edges_two_way(w, h)
+        s, r = _mesh_edges(w, h, directed)
         n, e = w * h, s.numel()
         weights = {k: t.clone().requires_grad_(True) for k, t in
                    synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), 3).items()}
@@ -126,12 +136,13 @@ def _worker(rank, world, port, tmpdir):
         dist.destroy_process_group()
 
 
-def test_two_rank_halo_exchange_matches_single_process(tmp_path):
+@pytest.mark.parametrize("directed", [False, True])
+def test_two_rank_halo_exchange_matches_single_process(tmp_path, directed):
     world = 2
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if directed else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), directed), nprocs=world, join=True)
     w, h, layers = 9, 8, 2
-    s, r = synthetic.grid_edges_two_way(w, h)
+    s, r = _mesh_edges(w, h, directed)
     n, e = w * h, s.numel()
     weights = {k: t.clone().requires_grad_(True) for k, t in
                synthetic.seeded_state_dict(synthetic.processor_shapes(layers, ["mesh_edges"], "sum"), 3).items()}
