@@ -1034,7 +1034,7 @@ def run_reference(args):
     aggregator = args.aggregator or default_agg
     step, e, kind = cpu_state(sample, aggregator)
     layers = sample[3]
-    warm = max(1, min(args.warmup, 2))
+    warm = max(1, min(args.warmup, 8))                         # W warm-up passes as asked (a pass is ~1.7 s on 16 cores; capped at 8)
     for _ in range(warm):
         step()
     steps = max(1, args.steps)
