@@ -198,8 +198,8 @@ class EdgeStorageOrder:
 
 class _PermuteRows(torch.autograd.Function):
     """``x[index]`` for a PERMUTATION ``index`` through the row-gather kernel, forward and backward (``torch.index_select`` would run its
-    backward as an atomic ``index_add_``: ~10 x the time on a 6 M x 128 tensor).  CUDA tensors go through ``hgn_rows_gather``; a CPU
-    tensor (host-side tests of the bookkeeping) through ``index_select`` on both sides."""
+    backward as an atomic ``index_add_``: ~10 x the time on a 6 M x 128 tensor).  CUDA only, like every kernel of the package; the
+    host-side test of the bookkeeping installs its own stand-in for ``_permute_rows`` (tests/test_graph_building_cpu.py)."""
 
     @staticmethod
     def forward(ctx, x, index32, inverse32):
@@ -212,9 +212,8 @@ class _PermuteRows(torch.autograd.Function):
 
 
 def _permute_rows(x: torch.Tensor, index32: torch.Tensor) -> torch.Tensor:
-    if not x.is_cuda:
-        return x.index_select(0, index32.long())
     from . import _cabi
+    _cabi.require_cuda(x, index32)
     x = x.contiguous()
     out = torch.empty_like(x)
     if x.shape[0]:
