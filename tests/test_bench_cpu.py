@@ -101,3 +101,21 @@ def test_cfg3_plate_clustering_and_batched_graph(monkeypatch):
     for es in graph.edge_sets:
         assert es.features.shape == (es.senders.numel(), 128) and int(es.senders.min()) >= 0
         assert int(max(es.senders.max(), es.receivers.max())) < n + sizes["hyper_nodes"]
+
+
+def test_clock_sampler_summary_from_nvml_and_nvidia_smi_rows():
+    """The `clocks` object of the bench line: median SM clock, max clock and the set of active clock-event reasons, from NVML samples
+    (numbers + 'Active' / 'Not Active') and from `nvidia-smi --format=csv` rows (strings); 'unavailable' without samples or a GPU."""
+    s = bench.ClockSampler(0)
+    assert s.summary() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    s.rows = [[1965.0, 1965.0, "Not Active", "Not Active", "Not Active", "Not Active"],
+              [1890.0, 1965.0, "Not Active", "Not Active", "Not Active", "Active"],
+              [1875.0, 1965.0, "Not Active", "Not Active", "Not Active", "Active"]]
+    out = s.summary()
+    assert out["sm_mhz"] == 1890.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 3
+    s.rows = [["1965", "1965", "Not Active", "Active", "Not Active", "Not Active"], ["[N/A]", "x"], ["1200", "1965", "Active", "Not Active", "Not Active", "Not Active"]]
+    out = s.summary()
+    assert out["samples"] == 2 and out["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
+    with bench.ClockSampler(0) as live:                  # no GPU here: both back ends are absent, the bench line still gets an object
+        pass
+    assert live.summary()["reasons"] == ["unavailable"] or live.summary()["sm_mhz"] is not None
